@@ -1,0 +1,167 @@
+// Decode-step kernels over the persistent KV cache (HBM-bound).
+//
+// The reference has no KV cache: it re-runs the whole decoder over the whole prefix and re-projects the
+// cross-attention K/V on every step (use_cache=False hard-wired, models/visual_dialog_decoder.py:64; loop at
+// models/visual_dialog_model.py:86-110).  Here each step processes ONE new position per beam row:
+//   dec_self_attn  : appends the new K/V at position *d_step and attends over positions 0..*d_step
+//   dec_cross_attn : every beam row of an image attends over that image's cross K/V (stored once per image)
+//   reorder_cache  : in-place beam gather, the semantic of _reorder_cache / index_select(0, beam_idx)
+//                    (models/visual_dialog_decoder.py:29-31,177-181)
+// Layouts:  self cache  [layer][k|v][image][position][beam][hidden]   (a beam gather touches contiguous rows)
+//           cross cache [layer][image][k|v, head][position][head_dim]  (one contiguous block per (image, head))
+#include <stdexcept>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gstvd {
+
+namespace {
+
+constexpr int kMaxSteps = 32;     // one score per lane
+constexpr int kMaxBeams = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+dec_self_attn_kernel(DecodeGeom g, int layer, const T* __restrict__ qkv, T* __restrict__ cache, const int* __restrict__ d_step,
+                     T* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x;
+  const int h = blockIdx.y * 4 + warp;
+  if (h >= g.heads) return;
+  const int b = row / g.K, kb = row - b * g.K;
+  const int step = *d_step;
+  const int H = g.H, D = g.D;
+  const int nd = D / 32;                       // dims per lane (2 for D=64, 4 for D=128)
+  const T* qrow = qkv + (int64_t)row * 3 * H + h * D;
+  float q[4], kn[4], vn[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (u < nd) {
+      const int d = lane + 32 * u;
+      q[u] = to_f32(qrow[d]); kn[u] = to_f32(qrow[H + d]); vn[u] = to_f32(qrow[2 * H + d]);
+    } else { q[u] = kn[u] = vn[u] = 0.f; }
+  }
+  // cache row of (kv, position t) for this beam/head
+  auto cache_ptr = [&](int kv, int t) -> T* {
+    return cache + (((((int64_t)layer * 2 + kv) * g.B + b) * g.T + t) * g.K + kb) * H + h * D;
+  };
+  {
+    T* kc = cache_ptr(0, step); T* vc = cache_ptr(1, step);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (u < nd) { kc[lane + 32 * u] = from_f32<T>(kn[u]); vc[lane + 32 * u] = from_f32<T>(vn[u]); }
+  }
+  // In bf16 mode the reference-equivalent value of the new key/value is the ROUNDED one (it is what later steps read)
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { kn[u] = to_f32(from_f32<T>(kn[u])); vn[u] = to_f32(from_f32<T>(vn[u])); }
+
+  const float scale_div = sqrtf((float)D);
+  float my_score = -INFINITY;
+  for (int t = 0; t <= step; ++t) {
+    float part = 0.f;
+    if (t == step) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) part = fmaf(q[u], kn[u], part);
+    } else {
+      const T* kc = cache_ptr(0, t);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (u < nd) part = fmaf(q[u], to_f32(kc[lane + 32 * u]), part);
+    }
+    const float s = warp_sum(part) / scale_div;
+    if (lane == t) my_score = s;
+  }
+  const float mx = warp_max(my_score);
+  const float e = (lane <= step) ? expf(my_score - mx) : 0.f;
+  const float sum = warp_sum(e);
+  const float pr = e / sum;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int t = 0; t <= step; ++t) {
+    const float pt = __shfl_sync(0xffffffffu, pr, t);
+    if (t == step) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = fmaf(pt, vn[u], acc[u]);
+    } else {
+      const T* vc = cache_ptr(1, t);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (u < nd) acc[u] = fmaf(pt, to_f32(vc[lane + 32 * u]), acc[u]);
+    }
+  }
+  T* o = out + (int64_t)row * H + h * D;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (u < nd) o[lane + 32 * u] = from_f32<T>(acc[u]);
+}
+
+// One CTA per (image, layer*2+kv).  Thread-local dependency only: every thread loads the K source values of its
+// column chunk before it stores any of them, so duplicated parents (beam_idx is not a permutation) are safe in place.
+template <typename T>
+__global__ void __launch_bounds__(256)
+reorder_cache_kernel(DecodeGeom g, T* __restrict__ cache, const int32_t* __restrict__ beam_idx, const int* __restrict__ d_len,
+                     int len_host, const uint8_t* __restrict__ d_skip) {
+  const int b = blockIdx.x, lk = blockIdx.y;
+  if (d_skip && d_skip[b]) return;
+  const int len = d_len ? (*d_len + 1) : len_host;
+  int parent[kMaxBeams];
+  bool moved = false;
+#pragma unroll
+  for (int k = 0; k < kMaxBeams; ++k) {
+    parent[k] = (k < g.K) ? beam_idx[b * g.K + k] : k;
+    moved |= (parent[k] != k);
+  }
+  if (!moved) return;
+  const int chunks = g.H / 8;
+  T* base = cache + ((int64_t)lk * g.B + b) * g.T * g.K * g.H;
+  for (int i = threadIdx.x; i < len * chunks; i += blockDim.x) {
+    const int t = i / chunks, c = (i - t * chunks) * 8;
+    T* p = base + (int64_t)t * g.K * g.H + c;
+    float vals[kMaxBeams][8];
+#pragma unroll
+    for (int k = 0; k < kMaxBeams; ++k)
+      if (k < g.K && parent[k] != k) Vec8<T>::load(p + (int64_t)parent[k] * g.H, vals[k]);
+#pragma unroll
+    for (int k = 0; k < kMaxBeams; ++k)
+      if (k < g.K && parent[k] != k) Vec8<T>::store(p + (int64_t)k * g.H, vals[k]);
+  }
+}
+
+}  // namespace
+
+int launch_dec_self_attn(int dtype, const DecodeGeom& g, int layer, const void* qkv, void* self_cache, const int* d_step,
+                         void* out, cudaStream_t stream) {
+  if (g.D != 64 && g.D != 128) throw std::runtime_error("dec_self_attn: head_dim must be 64 or 128");
+  if (g.T > kMaxSteps) throw std::runtime_error("dec_self_attn: at most 32 cached positions");
+  dim3 grid(g.B * g.K, (g.heads + 3) / 4);
+  if (dtype == kF32) dec_self_attn_kernel<float><<<grid, 128, 0, stream>>>(g, layer, (const float*)qkv, (float*)self_cache, d_step, (float*)out);
+  else dec_self_attn_kernel<bf16><<<grid, 128, 0, stream>>>(g, layer, (const bf16*)qkv, (bf16*)self_cache, d_step, (bf16*)out);
+  return 1;
+}
+
+int launch_dec_cross_attn(int dtype, const DecodeGeom& g, int layer, const void* q, const void* cross_cache,
+                          const float* enc_mask, void* out, cudaStream_t stream) {
+  const int64_t esz = dtype == kF32 ? 4 : 2;
+  const int64_t per_image = (int64_t)2 * g.heads * g.Le * g.D;
+  const char* kbase = (const char*)cross_cache + ((int64_t)layer * g.B) * per_image * esz;
+  AttnArgs a;
+  a.q = q; a.q_bs = g.H; a.q_hs = g.D; a.q_rs = 0;
+  a.k = kbase; a.k_bs = per_image; a.k_hs = (int64_t)g.Le * g.D; a.k_rs = g.D;
+  a.v = kbase + (int64_t)g.heads * g.Le * g.D * esz; a.v_bs = per_image; a.v_hs = a.k_hs; a.v_rs = g.D;
+  a.o = out; a.o_bs = g.H; a.o_hs = g.D; a.o_rs = 0;
+  a.kmask = enc_mask; a.kmask_bs = g.Le; a.neg = -1e9f; a.causal = 0;
+  a.B = g.B * g.K; a.H = g.heads; a.Lq = 1; a.Lk = g.Le; a.D = g.D; a.kv_batch_div = g.K;
+  return launch_attention_generic(a, dtype, stream);
+}
+
+int launch_reorder_cache(int dtype, const DecodeGeom& g, void* self_cache, const int32_t* beam_idx, const int* d_len,
+                         int len_host, const uint8_t* d_skip, cudaStream_t stream) {
+  if (g.K > kMaxBeams) throw std::runtime_error("reorder_cache: at most 8 beams");
+  if (g.H % 8) throw std::runtime_error("reorder_cache: hidden % 8 != 0");
+  dim3 grid(g.B, g.layers * 2);
+  if (dtype == kF32) reorder_cache_kernel<float><<<grid, 256, 0, stream>>>(g, (float*)self_cache, beam_idx, d_len, len_host, d_skip);
+  else reorder_cache_kernel<bf16><<<grid, 256, 0, stream>>>(g, (bf16*)self_cache, beam_idx, d_len, len_host, d_skip);
+  return 1;
+}
+
+}  // namespace gstvd

@@ -1,0 +1,989 @@
+// gstvd engine: context (packed weights, workspace, KV caches, CUDA graphs), orchestration of the encoder / decoder
+// kernels and the extern "C" boundary declared in include/gstvd.h.
+//
+// Schedule and arithmetic follow SURVEY.md appendix A, i.e. models/vilbert_dialog.py:806-912 (interleaved text /
+// image / connection layers), models/visual_dialog_model.py:131-135 (fusion) and the HF BertLayer decoder
+// (call site models/visual_dialog_decoder.py:300-311).
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/gstvd.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace gstvd;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+#define CUDA_CHECK(expr)                                                                          \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr); \
+  } while (0)
+
+struct InvalidArg : std::runtime_error { using std::runtime_error::runtime_error; };
+struct StateError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct Unsupported : std::runtime_error { using std::runtime_error::runtime_error; };
+
+std::string fmt(const char* f, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, f); vsnprintf(buf, sizeof buf, f, ap); va_end(ap);
+  return buf;
+}
+
+struct Linear { int out = 0, in = 0; float* w32 = nullptr; float* b = nullptr; bf16* w16 = nullptr; };
+struct LNp { int n = 0; float* g = nullptr; float* b = nullptr; };
+struct SelfLayer { Linear qkv, o, f1, f2; LNp ln_att, ln_out; };
+struct ConnLayer { Linear qkv1, qkv2, dense1, dense2, v_f1, v_f2, t_f1, t_f2; LNp ln1, ln2, v_ln, t_ln; };
+struct DecLayer { Linear qkv, o, cq, co, f1, f2; LNp ln_att, ln_cross, ln_out; };
+struct Slot { float* dst; int64_t numel; bool loaded; };
+
+struct DevBuf {
+  void* p = nullptr; size_t bytes = 0;
+  void alloc(size_t n) { if (n == 0) n = 16; CUDA_CHECK(cudaMalloc(&p, n)); bytes = n; }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct GraphKey {
+  int B, K, mode, T, top_k, ngram, Lh; float temperature, top_p; const void* hist_ids; const void* hist_seg;
+  bool operator<(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) < 0; }
+};
+
+}  // namespace
+
+struct gstvd_ctx {
+  gstvd_config cfg;
+  int device = 0, num_sms = 148, dtype = kF32;
+  size_t esz = 4;
+  std::string last_error;
+  int64_t launches = 0;
+  bool finalized = false;
+
+  // geometry
+  int H, Hv, Hb, heads, heads_v, heads_b, F, Fv, V, Vpad, Lt_max, Lv_max, Le_max, B_max, T_max, K_max, Ldec_max;
+  int dec_layers, dec_heads, dec_F;
+
+  // weights
+  DevBuf mat32, mat16, vec32;
+  size_t mat_elems = 0, vec_elems = 0;
+  std::unordered_map<std::string, Slot> slots;
+  float *word = nullptr, *pos = nullptr, *type = nullptr, *type_ext = nullptr; LNp emb_ln;
+  Linear img_emb; float *loc_w = nullptr, *loc_b = nullptr; LNp img_ln;
+  std::vector<SelfLayer> t_layers, v_layers;
+  std::vector<ConnLayer> c_layers;
+  Linear t_pool, v_pool, nsp_head, fc_l, fc_v;
+  std::vector<DecLayer> d_layers;
+  Linear cross_kv;      // all decoder layers' crossattention.self.{key,value}: [layers*2*H, H]
+  Linear lm_head;
+
+  // workspace (element type = compute dtype unless noted)
+  DevBuf xt, yt, xv, yv, qkv_t, qkv_v, ctx_t, ctx_v, tmp_t, tmp_v, ffn_t, ffn_v, feat_cast, fused, pool;
+  DevBuf fused_mask;                                  // fp32 [B, Le]
+  DevBuf dh, da, db, dqkv, dctx, dtmp, dffn, dqc;      // decoder activations, rows = max(B*K, B*Ldec)
+  DevBuf logits;                                      // fp32 [rows, Vpad]
+  DevBuf cross_cache, self_cache;
+  DevBuf labels;                                      // int64 [B*Ldec]
+  DevBuf sel_val, sel_idx, logz;                      // [rows, kSelMax]
+  DevBuf ban_tokens, ban_count, prefix, seq;          // sample-mode state
+  DevBuf beam_scores, beam_tokens, cur_tokens, beam_idx, beam_done, hyp_score, hyp_len, hyp_tokens, hyp_count, hyp_worst;
+  DevBuf d_step, d_seed;
+  int enc_B = 0, enc_Le = 0;        // shape of the resident fused states
+  int cross_B = 0, cross_Le = 0;    // shape of the resident cross K/V
+  // beam op-test state
+  int op_B = 0, op_K = 0, op_T = 0;
+
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  cudaStream_t own_stream = nullptr;     // decode steps run (and are graph-captured) here: the caller may be on the legacy stream
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+
+  size_t act_bytes(size_t elems) const { return elems * esz; }
+};
+
+namespace {
+
+// ---- weight layout ----------------------------------------------------------------------------------------------
+struct Planner {
+  gstvd_ctx* c;
+  std::vector<std::pair<float**, size_t>> mats, vecs;   // deferred pointer fix-ups: (where, offset)
+  size_t mat_off = 0, vec_off = 0;
+  struct Pending { std::string name; bool mat; size_t off; int64_t numel; };
+  std::vector<Pending> pend;
+
+  size_t take_mat(size_t n) { size_t o = mat_off; mat_off += (n + 63) & ~size_t(63); return o; }
+  size_t take_vec(size_t n) { size_t o = vec_off; vec_off += (n + 63) & ~size_t(63); return o; }
+
+  // Linear whose rows are the concatenation of several nn.Linear modules (fused q/k/v etc.)
+  void linear(Linear& L, int in, const std::vector<std::pair<std::string, int>>& parts) {
+    int out = 0;
+    for (auto& p : parts) out += p.second;
+    L.out = out; L.in = in;
+    size_t wo = take_mat((size_t)out * in), bo = take_vec(out);
+    mats.push_back({&L.w32, wo}); vecs.push_back({&L.b, bo});
+    int r = 0;
+    for (auto& p : parts) {
+      pend.push_back({p.first + ".weight", true, wo + (size_t)r * in, (int64_t)p.second * in});
+      pend.push_back({p.first + ".bias", false, bo + r, p.second});
+      r += p.second;
+    }
+  }
+  void linear1(Linear& L, const std::string& name, int out, int in) { linear(L, in, {{name, out}}); }
+  void ln(LNp& l, const std::string& name, int n) {
+    l.n = n;
+    size_t go = take_vec(n), bo = take_vec(n);
+    vecs.push_back({&l.g, go}); vecs.push_back({&l.b, bo});
+    pend.push_back({name + ".weight", false, go, n});
+    pend.push_back({name + ".bias", false, bo, n});
+  }
+  void table(float*& ptr, const std::string& name, int64_t numel) {
+    size_t o = take_vec(numel);
+    vecs.push_back({&ptr, o});
+    pend.push_back({name, false, o, numel});
+  }
+};
+
+void plan_weights(gstvd_ctx* c) {
+  const gstvd_config& g = c->cfg;
+  Planner P{c};
+  const std::string E = "encoder.bert_pretrained.bert.";
+  const int H = c->H, Hv = c->Hv, Hb = c->Hb;
+  P.table(c->word, E + "embeddings.word_embeddings.weight", (int64_t)g.vocab_size * H);
+  P.table(c->pos, E + "embeddings.position_embeddings.weight", (int64_t)g.max_position_embeddings * H);
+  P.table(c->type, E + "embeddings.token_type_embeddings.weight", (int64_t)g.type_vocab_size * H);
+  P.table(c->type_ext, E + "embeddings.token_type_embeddings_extension.weight", (int64_t)10 * H);
+  P.ln(c->emb_ln, E + "embeddings.LayerNorm", H);
+  P.linear1(c->img_emb, E + "v_embeddings.image_embeddings", Hv, g.v_feature_size);
+  P.table(c->loc_w, E + "v_embeddings.image_location_embeddings.weight", (int64_t)Hv * 5);
+  P.table(c->loc_b, E + "v_embeddings.image_location_embeddings.bias", Hv);
+  P.ln(c->img_ln, E + "v_embeddings.LayerNorm", Hv);
+  auto self_layer = [&](SelfLayer& L, const std::string& p, int h, int f) {
+    P.linear(L.qkv, h, {{p + "attention.self.query", h}, {p + "attention.self.key", h}, {p + "attention.self.value", h}});
+    P.linear1(L.o, p + "attention.output.dense", h, h);
+    P.ln(L.ln_att, p + "attention.output.LayerNorm", h);
+    P.linear1(L.f1, p + "intermediate.dense", f, h);
+    P.linear1(L.f2, p + "output.dense", h, f);
+    P.ln(L.ln_out, p + "output.LayerNorm", h);
+  };
+  c->t_layers.resize(g.num_hidden_layers);
+  for (int i = 0; i < g.num_hidden_layers; ++i) self_layer(c->t_layers[i], E + "encoder.layer." + std::to_string(i) + ".", H, c->F);
+  c->v_layers.resize(g.v_num_hidden_layers);
+  for (int i = 0; i < g.v_num_hidden_layers; ++i) self_layer(c->v_layers[i], E + "encoder.v_layer." + std::to_string(i) + ".", Hv, c->Fv);
+  c->c_layers.resize(g.num_connections);
+  for (int i = 0; i < g.num_connections; ++i) {
+    ConnLayer& L = c->c_layers[i];
+    const std::string p = E + "encoder.c_layer." + std::to_string(i) + ".";
+    P.linear(L.qkv1, Hv, {{p + "biattention.query1", Hb}, {p + "biattention.key1", Hb}, {p + "biattention.value1", Hb}});
+    P.linear(L.qkv2, H, {{p + "biattention.query2", Hb}, {p + "biattention.key2", Hb}, {p + "biattention.value2", Hb}});
+    P.linear1(L.dense1, p + "biOutput.dense1", Hv, Hb);
+    P.ln(L.ln1, p + "biOutput.LayerNorm1", Hv);
+    P.linear1(L.dense2, p + "biOutput.dense2", H, Hb);
+    P.ln(L.ln2, p + "biOutput.LayerNorm2", H);
+    P.linear1(L.v_f1, p + "v_intermediate.dense", c->Fv, Hv);
+    P.linear1(L.v_f2, p + "v_output.dense", Hv, c->Fv);
+    P.ln(L.v_ln, p + "v_output.LayerNorm", Hv);
+    P.linear1(L.t_f1, p + "t_intermediate.dense", c->F, H);
+    P.linear1(L.t_f2, p + "t_output.dense", H, c->F);
+    P.ln(L.t_ln, p + "t_output.LayerNorm", H);
+  }
+  P.linear1(c->t_pool, E + "t_pooler.dense", Hb, H);
+  P.linear1(c->v_pool, E + "v_pooler.dense", Hb, Hv);
+  P.linear1(c->nsp_head, "encoder.bert_pretrained.cls.bi_seq_relationship", 2, Hb);
+  if (c->dec_layers > 0) {
+    P.linear1(c->fc_l, "vlfusion.fc_l", H, H);
+    P.linear1(c->fc_v, "vlfusion.fc_v", H, Hv);
+    const std::string D = "decoder.decoder.bert.encoder.layer.";
+    c->d_layers.resize(c->dec_layers);
+    std::vector<std::pair<std::string, int>> kv_parts;
+    for (int i = 0; i < c->dec_layers; ++i) {
+      DecLayer& L = c->d_layers[i];
+      const std::string p = D + std::to_string(i) + ".";
+      P.linear(L.qkv, H, {{p + "attention.self.query", H}, {p + "attention.self.key", H}, {p + "attention.self.value", H}});
+      P.linear1(L.o, p + "attention.output.dense", H, H);
+      P.ln(L.ln_att, p + "attention.output.LayerNorm", H);
+      P.linear1(L.cq, p + "crossattention.self.query", H, H);
+      kv_parts.push_back({p + "crossattention.self.key", H});
+      kv_parts.push_back({p + "crossattention.self.value", H});
+      P.linear1(L.co, p + "crossattention.output.dense", H, H);
+      P.ln(L.ln_cross, p + "crossattention.output.LayerNorm", H);
+      P.linear1(L.f1, p + "intermediate.dense", c->dec_F, H);
+      P.linear1(L.f2, p + "output.dense", H, c->dec_F);
+      P.ln(L.ln_out, p + "output.LayerNorm", H);
+    }
+    P.linear(c->cross_kv, H, kv_parts);
+    // lm_head.decoder.weight / lm_head.bias (lm_head.decoder.bias is the same tensor, visual_dialog_decoder.py:333-335)
+    c->lm_head.out = g.vocab_size; c->lm_head.in = H;
+    size_t wo = P.take_mat((size_t)g.vocab_size * H), bo = P.take_vec(g.vocab_size);
+    P.mats.push_back({&c->lm_head.w32, wo}); P.vecs.push_back({&c->lm_head.b, bo});
+    P.pend.push_back({"decoder.decoder.lm_head.decoder.weight", true, wo, (int64_t)g.vocab_size * H});
+    P.pend.push_back({"decoder.decoder.lm_head.bias", false, bo, g.vocab_size});
+  }
+  c->mat_elems = P.mat_off; c->vec_elems = P.vec_off;
+  c->mat32.alloc(c->mat_elems * 4);
+  c->vec32.alloc(c->vec_elems * 4);
+  CUDA_CHECK(cudaMemset(c->mat32.p, 0, c->mat32.bytes));
+  CUDA_CHECK(cudaMemset(c->vec32.p, 0, c->vec32.bytes));
+  if (c->dtype == kBF16) c->mat16.alloc(c->mat_elems * 2);
+  for (auto& m : P.mats) *m.first = (float*)c->mat32.p + m.second;
+  for (auto& v : P.vecs) *v.first = (float*)c->vec32.p + v.second;
+  for (auto& p : P.pend) {
+    float* base = p.mat ? (float*)c->mat32.p : (float*)c->vec32.p;
+    c->slots[p.name] = Slot{base + p.off, p.numel, false};
+  }
+}
+
+void set_w16(gstvd_ctx* c, Linear& L) { if (L.w32) L.w16 = (bf16*)c->mat16.p + (L.w32 - (float*)c->mat32.p); }
+
+void assign_w16(gstvd_ctx* c) {
+  set_w16(c, c->img_emb);
+  for (auto& L : c->t_layers) { set_w16(c, L.qkv); set_w16(c, L.o); set_w16(c, L.f1); set_w16(c, L.f2); }
+  for (auto& L : c->v_layers) { set_w16(c, L.qkv); set_w16(c, L.o); set_w16(c, L.f1); set_w16(c, L.f2); }
+  for (auto& L : c->c_layers) {
+    set_w16(c, L.qkv1); set_w16(c, L.qkv2); set_w16(c, L.dense1); set_w16(c, L.dense2);
+    set_w16(c, L.v_f1); set_w16(c, L.v_f2); set_w16(c, L.t_f1); set_w16(c, L.t_f2);
+  }
+  set_w16(c, c->t_pool); set_w16(c, c->v_pool); set_w16(c, c->nsp_head); set_w16(c, c->fc_l); set_w16(c, c->fc_v);
+  for (auto& L : c->d_layers) { set_w16(c, L.qkv); set_w16(c, L.o); set_w16(c, L.cq); set_w16(c, L.co); set_w16(c, L.f1); set_w16(c, L.f2); }
+  set_w16(c, c->cross_kv); set_w16(c, c->lm_head);
+}
+
+// Known checkpoint keys the path does not read.
+bool is_ignored_key(const std::string& n) {
+  static const char* pats[] = {".q_dense1.", ".q_dense2.", "sep_embeddings", "cls.predictions.", "cls.imagePredictions.",
+                               "position_ids"};
+  for (auto p : pats) if (n.find(p) != std::string::npos) return true;
+  return false;
+}
+
+std::string canonical_name(const std::string& n) {
+  const std::string de = "decoder.decoder.bert.embeddings.";
+  if (n.compare(0, de.size(), de) == 0) return "encoder.bert_pretrained.bert.embeddings." + n.substr(de.size());
+  if (n == "decoder.decoder.lm_head.decoder.bias") return "decoder.decoder.lm_head.bias";
+  return n;
+}
+
+void alloc_workspace(gstvd_ctx* c) {
+  const size_t B = c->B_max, Lt = c->Lt_max, Lv = c->Lv_max, Le = c->Le_max;
+  const size_t Mt = B * Lt, Mv = B * Lv;
+  const size_t H = c->H, Hv = c->Hv, Hb = c->Hb;
+  auto A = [&](DevBuf& b, size_t elems) { b.alloc(c->act_bytes(elems)); };
+  const size_t wt = std::max(H, Hb), wv = std::max(Hv, Hb);
+  A(c->xt, Mt * H); A(c->yt, Mt * H); A(c->xv, Mv * Hv); A(c->yv, Mv * Hv);
+  A(c->qkv_t, Mt * 3 * wt); A(c->qkv_v, Mv * 3 * wv);
+  A(c->ctx_t, Mt * wt); A(c->ctx_v, Mv * wv);
+  A(c->tmp_t, Mt * wt); A(c->tmp_v, Mv * std::max(wv, H));
+  A(c->ffn_t, Mt * c->F); A(c->ffn_v, Mv * c->Fv);
+  A(c->feat_cast, Mv * c->cfg.v_feature_size);
+  A(c->fused, B * Le * H);
+  A(c->pool, B * (H + Hv + 3 * Hb + 8));
+  c->fused_mask.alloc(B * Le * 4);
+  if (c->dec_layers > 0) {
+    const size_t K = c->K_max, T = c->T_max;
+    const size_t R = std::max(B * K, B * (size_t)c->Ldec_max);
+    A(c->dh, R * H); A(c->da, R * H); A(c->db, R * H); A(c->dqkv, R * 3 * H); A(c->dctx, R * H); A(c->dtmp, R * H);
+    A(c->dffn, R * c->dec_F); A(c->dqc, R * H);
+    c->logits.alloc(R * (size_t)c->Vpad * 4);
+    A(c->cross_cache, (size_t)c->dec_layers * B * 2 * H * Le);
+    A(c->self_cache, (size_t)c->dec_layers * 2 * B * T * K * H);
+    c->labels.alloc(B * (size_t)c->Ldec_max * 8);
+    c->sel_val.alloc(R * kSelMax * 4); c->sel_idx.alloc(R * kSelMax * 4); c->logz.alloc(R * 4);
+    c->ban_tokens.alloc(B * Lt * 4); c->ban_count.alloc(B * 4);
+    c->prefix.alloc(B * (T + 1) * 4); c->seq.alloc(B * T * 4);
+    c->beam_scores.alloc(B * K * 4); c->beam_tokens.alloc(2 * B * K * T * 4); c->cur_tokens.alloc(R * 4);
+    c->beam_idx.alloc(B * K * 4); c->beam_done.alloc(B); c->hyp_score.alloc(B * (K + 1) * 8);
+    c->hyp_len.alloc(B * (K + 1) * 4); c->hyp_tokens.alloc(B * (K + 1) * T * 4); c->hyp_count.alloc(B * 4);
+    c->hyp_worst.alloc(B * 8);
+  }
+  c->d_step.alloc(16); c->d_seed.alloc(16);
+  CUDA_CHECK(cudaMemset(c->d_step.p, 0, 16));
+}
+
+// ---- op wrappers ---------------------------------------------------------------------------------------------------
+struct Exec {
+  gstvd_ctx* c; cudaStream_t s;
+  int dt() const { return c->dtype; }
+
+  void gemm(const void* A, int64_t lda, const Linear& L, void* C, int64_t ldc, int M, int act = 0, bool out_f32 = false,
+            int hm_D = 0, int hm_L = 0, int hm_G = 0, int hm_B = 0) {
+    GemmArgs a;
+    a.A = A; a.lda = lda; a.ldw = L.in; a.bias = L.b; a.C = C; a.ldc = ldc; a.out_f32 = out_f32 ? 1 : 0; a.act = act;
+    a.M = M; a.N = L.out; a.K = L.in; a.hm_D = hm_D; a.hm_L = hm_L; a.hm_G = hm_G; a.hm_B = hm_B;
+    if (c->dtype == kF32) { a.W = L.w32; c->launches += launch_gemm_simt(a, kF32, s); }
+    else {
+      a.W = L.w16;
+      if (c->cfg.flags & GSTVD_FLAG_DEBUG_SIMT_GEMM) c->launches += launch_gemm_simt(a, kBF16, s);
+      else c->launches += launch_gemm_tc(a, c->num_sms, s);
+    }
+  }
+  void add_ln(const void* x, const void* res, const LNp& l, void* y, int rows) {
+    c->launches += launch_add_layernorm(dt(), rows, l.n, x, l.n, res, l.n, l.g, l.b, y, l.n, s);
+  }
+  // q/k/v: rows of `ld` elements holding all heads; one batch = L rows
+  void attention(const void* q, int64_t ldq, int Lq, const void* k, const void* v, int64_t ldkv, int Lk, void* o, int64_t ldo,
+                 int B, int heads, int D, const float* kmask, float neg, int causal) {
+    AttnArgs a;
+    a.q = q; a.q_bs = (int64_t)Lq * ldq; a.q_hs = D; a.q_rs = ldq;
+    a.k = k; a.k_bs = (int64_t)Lk * ldkv; a.k_hs = D; a.k_rs = ldkv;
+    a.v = v; a.v_bs = (int64_t)Lk * ldkv; a.v_hs = D; a.v_rs = ldkv;
+    a.o = o; a.o_bs = (int64_t)Lq * ldo; a.o_hs = D; a.o_rs = ldo;
+    a.kmask = kmask; a.kmask_bs = Lk; a.neg = neg; a.causal = causal;
+    a.B = B; a.H = heads; a.Lq = Lq; a.Lk = Lk; a.D = D; a.kv_batch_div = 1;
+    c->launches += launch_attention_generic(a, dt(), s);
+  }
+  char* off(void* p, size_t elems) const { return (char*)p + elems * c->esz; }
+  const char* off(const void* p, size_t elems) const { return (const char*)p + elems * c->esz; }
+};
+
+void self_layer_fwd(Exec& X, const SelfLayer& L, void* x, void* y, void* qkv, void* ctx, void* tmp, void* ffn, int B, int Lq,
+                    int heads, const float* mask) {
+  gstvd_ctx* c = X.c;
+  const int h = L.o.out, M = B * Lq, D = h / heads;
+  X.gemm(x, h, L.qkv, qkv, 3 * h, M);
+  X.attention(qkv, 3 * h, Lq, X.off(qkv, h), X.off(qkv, 2 * h), 3 * h, Lq, ctx, h, B, heads, D, mask, -10000.0f, 0);
+  X.gemm(ctx, h, L.o, tmp, h, M);
+  X.add_ln(tmp, x, L.ln_att, y, M);
+  X.gemm(y, h, L.f1, ffn, L.f1.out, M, 1);
+  X.gemm(ffn, L.f1.out, L.f2, tmp, h, M);
+  X.add_ln(tmp, y, L.ln_out, x, M);
+  (void)c;
+}
+
+void conn_layer_fwd(Exec& X, const ConnLayer& L, int B, int Lt, int Lv, const float* tmask, const float* vmask) {
+  gstvd_ctx* c = X.c;
+  const int H = c->H, Hv = c->Hv, Hb = c->Hb, D = Hb / c->heads_b, Mt = B * Lt, Mv = B * Lv;
+  void *xt = c->xt.p, *yt = c->yt.p, *xv = c->xv.p, *yv = c->yv.p;
+  void *qv = c->qkv_v.p, *qt = c->qkv_t.p;
+  X.gemm(xv, Hv, L.qkv1, qv, 3 * Hb, Mv);      // query1 | key1 | value1  (image stream)
+  X.gemm(xt, H, L.qkv2, qt, 3 * Hb, Mt);       // query2 | key2 | value2  (text stream)
+  // text queries over image keys/values -> ctx_t ; image queries over text keys/values -> ctx_v  (:671-710)
+  X.attention(qt, 3 * Hb, Lt, X.off(qv, Hb), X.off(qv, 2 * Hb), 3 * Hb, Lv, c->ctx_t.p, Hb, B, c->heads_b, D, vmask, -10000.0f, 0);
+  X.attention(qv, 3 * Hb, Lv, X.off(qt, Hb), X.off(qt, 2 * Hb), 3 * Hb, Lt, c->ctx_v.p, Hb, B, c->heads_b, D, tmask, -10000.0f, 0);
+  // BertBiOutput with the contexts swapped into the opposite stream (:765, :732-744)
+  X.gemm(c->ctx_v.p, Hb, L.dense1, c->tmp_v.p, Hv, Mv);
+  X.add_ln(c->tmp_v.p, xv, L.ln1, yv, Mv);
+  X.gemm(c->ctx_t.p, Hb, L.dense2, c->tmp_t.p, H, Mt);
+  X.add_ln(c->tmp_t.p, xt, L.ln2, yt, Mt);
+  X.gemm(yv, Hv, L.v_f1, c->ffn_v.p, c->Fv, Mv, 1);
+  X.gemm(c->ffn_v.p, c->Fv, L.v_f2, c->tmp_v.p, Hv, Mv);
+  X.add_ln(c->tmp_v.p, yv, L.v_ln, xv, Mv);
+  X.gemm(yt, H, L.t_f1, c->ffn_t.p, c->F, Mt, 1);
+  X.gemm(c->ffn_t.p, c->F, L.t_f2, c->tmp_t.p, H, Mt);
+  X.add_ln(c->tmp_t.p, yt, L.t_ln, xt, Mt);
+}
+
+void check_ready(gstvd_ctx* c) { if (!c->finalized) throw StateError("weights not finalized: call gstvd_finalize_weights first"); }
+
+void do_encode(gstvd_ctx* c, int B, int Lt, int Lv, const int64_t* ids, const int64_t* seg, const float* att, const float* feat,
+               const float* loc, const float* imask, float* out_t, float* out_v, float* out_fused, float* out_fused_mask,
+               float* out_nsp, cudaStream_t s) {
+  check_ready(c);
+  if (B < 1 || B > c->B_max || Lt < 1 || Lt > c->Lt_max || Lv < 1 || Lv > c->Lv_max)
+    throw InvalidArg(fmt("encode: shape B=%d Lt=%d Lv=%d exceeds capacity (%d, %d, %d)", B, Lt, Lv, c->B_max, c->Lt_max, c->Lv_max));
+  if (!ids || !feat || !loc) throw InvalidArg("encode: input_ids / image_feat / image_loc must not be NULL");
+  if (Lt > c->cfg.max_position_embeddings) throw InvalidArg("encode: Lt exceeds max_position_embeddings");
+  Exec X{c, s};
+  const int H = c->H, Hv = c->Hv, Mt = B * Lt, Mv = B * Lv;
+  c->launches += launch_embed_text(c->dtype, Mt, Lt, H, ids, seg, nullptr, 0, c->word, c->pos, c->type, c->type_ext,
+                                   c->cfg.type_vocab_size, c->emb_ln.g, c->emb_ln.b, c->xt.p, s);
+  const void* feat_in = feat;
+  if (c->dtype != kF32) {
+    c->launches += launch_cast_f32_to(c->dtype, feat, c->feat_cast.p, (int64_t)Mv * c->cfg.v_feature_size, s);
+    feat_in = c->feat_cast.p;
+  }
+  X.gemm(feat_in, c->cfg.v_feature_size, c->img_emb, c->tmp_v.p, Hv, Mv);
+  c->launches += launch_image_embed_ln(c->dtype, Mv, Hv, c->tmp_v.p, loc, c->loc_w, c->loc_b, c->img_ln.g, c->img_ln.b, c->xv.p, s);
+
+  auto text_layer = [&](int i) { self_layer_fwd(X, c->t_layers[i], c->xt.p, c->yt.p, c->qkv_t.p, c->ctx_t.p, c->tmp_t.p, c->ffn_t.p, B, Lt, c->heads, att); };
+  auto image_layer = [&](int i) { self_layer_fwd(X, c->v_layers[i], c->xv.p, c->yv.p, c->qkv_v.p, c->ctx_v.p, c->tmp_v.p, c->ffn_v.p, B, Lv, c->heads_v, imask); };
+  int v_start = 0, t_start = 0;
+  for (int n = 0; n < c->cfg.num_connections; ++n) {          // models/vilbert_dialog.py:831-905
+    const int v_end = c->cfg.v_biattention_id[n], t_end = c->cfg.t_biattention_id[n];
+    for (int i = v_start; i < v_end; ++i) image_layer(i);
+    for (int i = t_start; i < t_end; ++i) text_layer(i);
+    conn_layer_fwd(X, c->c_layers[n], B, Lt, Lv, att, imask);
+    v_start = v_end; t_start = t_end;
+  }
+  for (int i = v_start; i < c->cfg.v_num_hidden_layers; ++i) image_layer(i);
+  for (int i = t_start; i < c->cfg.num_hidden_layers; ++i) text_layer(i);
+
+  if (out_t) c->launches += launch_cast_to_f32(c->dtype, c->xt.p, out_t, (int64_t)Mt * H, s);
+  if (out_v) c->launches += launch_cast_to_f32(c->dtype, c->xv.p, out_v, (int64_t)Mv * Hv, s);
+  if (out_nsp) {
+    // poolers + bi_seq_relationship, fusion 'mul' (models/vilbert_dialog.py:915-941, :1030-1038)
+    const int Hb = c->Hb;
+    char* p = (char*)c->pool.p;
+    void* t0 = p; void* v0 = X.off(t0, (size_t)B * H); void* pt = X.off(v0, (size_t)B * Hv);
+    void* pv = X.off(pt, (size_t)B * Hb); void* pm = X.off(pv, (size_t)B * Hb);
+    c->launches += launch_gather_first_rows(c->dtype, B, Lt, H, c->xt.p, t0, s);
+    c->launches += launch_gather_first_rows(c->dtype, B, Lv, Hv, c->xv.p, v0, s);
+    X.gemm(t0, H, c->t_pool, pt, Hb, B);
+    X.gemm(v0, Hv, c->v_pool, pv, Hb, B);
+    c->launches += launch_relu_mul(c->dtype, (int64_t)B * Hb, pt, pv, pm, s);
+    X.gemm(pm, Hb, c->nsp_head, out_nsp, 2, B, 0, true);
+  }
+  if (c->dec_layers > 0) {
+    // VLFusion: cat(fc_v(v), fc_l(t)) with image rows first (models/visual_dialog_model.py:131-135)
+    X.gemm(c->xv.p, Hv, c->fc_v, c->tmp_v.p, H, Mv);
+    X.gemm(c->xt.p, H, c->fc_l, c->tmp_t.p, H, Mt);
+    c->launches += launch_concat_fused(c->dtype, B, Lv, Lt, H, c->tmp_v.p, c->tmp_t.p, c->fused.p, imask, att, (float*)c->fused_mask.p, s);
+    c->enc_B = B; c->enc_Le = Lv + Lt;
+    if (out_fused) c->launches += launch_cast_to_f32(c->dtype, c->fused.p, out_fused, (int64_t)B * (Lv + Lt) * H, s);
+    if (out_fused_mask) CUDA_CHECK(cudaMemcpyAsync(out_fused_mask, c->fused_mask.p, (size_t)B * (Lv + Lt) * 4, cudaMemcpyDeviceToDevice, s));
+  } else if (out_fused || out_fused_mask) {
+    throw InvalidArg("encode: fused outputs requested from an encoder-only context");
+  }
+}
+
+void do_prefill(gstvd_ctx* c, int B, int Le, const float* enc_hidden, const float* enc_mask, cudaStream_t s) {
+  check_ready(c);
+  if (c->dec_layers == 0) throw StateError("prefill_cross: encoder-only context");
+  if (B < 1 || B > c->B_max || Le < 1 || Le > c->Le_max) throw InvalidArg("prefill_cross: shape exceeds capacity");
+  Exec X{c, s};
+  const int H = c->H;
+  if (enc_hidden) {
+    c->launches += launch_cast_f32_to(c->dtype, enc_hidden, c->fused.p, (int64_t)B * Le * H, s);
+    if (enc_mask) CUDA_CHECK(cudaMemcpyAsync(c->fused_mask.p, enc_mask, (size_t)B * Le * 4, cudaMemcpyDeviceToDevice, s));
+    else {
+      std::vector<float> ones((size_t)B * Le, 1.f);
+      CUDA_CHECK(cudaMemcpyAsync(c->fused_mask.p, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    c->enc_B = B; c->enc_Le = Le;
+  } else if (c->enc_B != B || c->enc_Le != Le) {
+    throw StateError(fmt("prefill_cross: resident encoder states are [%d, %d], asked for [%d, %d]", c->enc_B, c->enc_Le, B, Le));
+  }
+  const int D = H / c->dec_heads;
+  // one GEMM for every layer's K and V, written head-major: [layer][image][kv*heads + h][Le][D]
+  X.gemm(c->fused.p, H, c->cross_kv, c->cross_cache.p, 0, B * Le, 0, false, D, Le, 2 * c->dec_heads, B);
+  c->cross_B = B; c->cross_Le = Le;
+}
+
+DecodeGeom make_geom(gstvd_ctx* c, int B, int K, int T) {
+  DecodeGeom g;
+  g.B = B; g.K = K; g.H = c->H; g.heads = c->dec_heads; g.D = c->H / c->dec_heads; g.layers = c->dec_layers; g.T = T; g.Le = c->cross_Le;
+  return g;
+}
+
+BeamBuffers beam_buffers(gstvd_ctx* c) {
+  BeamBuffers bb;
+  bb.beam_scores = (float*)c->beam_scores.p; bb.tokens = (int32_t*)c->beam_tokens.p; bb.cur_tokens = (int32_t*)c->cur_tokens.p;
+  bb.beam_idx = (int32_t*)c->beam_idx.p; bb.done = (uint8_t*)c->beam_done.p; bb.hyp_score = (double*)c->hyp_score.p;
+  bb.hyp_len = (int32_t*)c->hyp_len.p; bb.hyp_tokens = (int32_t*)c->hyp_tokens.p; bb.hyp_count = (int32_t*)c->hyp_count.p;
+  bb.hyp_worst = (double*)c->hyp_worst.p; bb.d_step = (int*)c->d_step.p;
+  return bb;
+}
+
+// One decode step for all M = B*K rows: embeddings -> 12 x [self-attn over cache, cross-attn, FFN] -> LM head -> selection.
+void decode_step(gstvd_ctx* c, const DecodeGeom& g, const gstvd_gen_params& gp, const int64_t* hist_ids, const int64_t* hist_seg,
+                 int Lh, cudaStream_t s) {
+  Exec X{c, s};
+  const int H = c->H, M = g.B * g.K;
+  const int* d_step = (const int*)c->d_step.p;
+  c->launches += launch_embed_step(c->dtype, M, H, (const int32_t*)c->cur_tokens.p, d_step, c->word, c->pos, c->type,
+                                   c->emb_ln.g, c->emb_ln.b, c->dh.p, s);
+  for (int l = 0; l < c->dec_layers; ++l) {
+    const DecLayer& L = c->d_layers[l];
+    X.gemm(c->dh.p, H, L.qkv, c->dqkv.p, 3 * H, M);
+    c->launches += launch_dec_self_attn(c->dtype, g, l, c->dqkv.p, c->self_cache.p, d_step, c->dctx.p, s);
+    X.gemm(c->dctx.p, H, L.o, c->dtmp.p, H, M);
+    X.add_ln(c->dtmp.p, c->dh.p, L.ln_att, c->da.p, M);
+    X.gemm(c->da.p, H, L.cq, c->dqc.p, H, M);
+    c->launches += launch_dec_cross_attn(c->dtype, g, l, c->dqc.p, c->cross_cache.p, (const float*)c->fused_mask.p, c->dctx.p, s);
+    X.gemm(c->dctx.p, H, L.co, c->dtmp.p, H, M);
+    X.add_ln(c->dtmp.p, c->da.p, L.ln_cross, c->db.p, M);
+    X.gemm(c->db.p, H, L.f1, c->dffn.p, c->dec_F, M, 1);
+    X.gemm(c->dffn.p, c->dec_F, L.f2, c->dtmp.p, H, M);
+    X.add_ln(c->dtmp.p, c->db.p, L.ln_out, c->dh.p, M);
+  }
+  X.gemm(c->dh.p, H, c->lm_head, c->logits.p, c->Vpad, M, 0, true);
+  float* sv = (float*)c->sel_val.p; int32_t* si = (int32_t*)c->sel_idx.p;
+  if (gp.mode == GSTVD_SELECT_BEAM) {
+    const int nsel = 2 * g.K;
+    c->launches += launch_row_select(M, c->V, (const float*)c->logits.p, c->Vpad, 0, (const float*)c->beam_scores.p, 1.f, nullptr,
+                                     nullptr, 0, nsel, sv, si, nullptr, s);
+    BeamBuffers bb = beam_buffers(c);
+    c->launches += launch_beam_step(bb, g.B, g.K, g.T, c->V, nsel, sv, si, 102, nullptr, nullptr, nullptr, s);
+    c->launches += launch_reorder_cache(c->dtype, g, c->self_cache.p, bb.beam_idx, d_step, 0, nullptr, s);
+  } else {
+    const int nsel = kSelMax;
+    const int32_t* bt = nullptr; const int32_t* bc = nullptr;
+    if (gp.ngram_blocking_size > 0) {
+      c->launches += launch_ngram_ban(M, Lh, hist_ids, hist_seg, (const int32_t*)c->prefix.p, g.T + 1, d_step, gp.ngram_blocking_size,
+                                      (int32_t*)c->ban_tokens.p, (int32_t*)c->ban_count.p, Lh, s);
+      bt = (const int32_t*)c->ban_tokens.p; bc = (const int32_t*)c->ban_count.p;
+    }
+    c->launches += launch_row_select(M, c->V, (const float*)c->logits.p, c->Vpad, 1, nullptr, gp.temperature, bt, bc, Lh, nsel, sv, si,
+                                     nullptr, s);
+    c->launches += launch_sample_step(M, g.T, nsel, sv, si, gp.top_k, gp.top_p, 0, (const uint64_t*)c->d_seed.p, d_step, 102, (int32_t*)c->seq.p,
+                                      (int32_t*)c->cur_tokens.p, (int32_t*)c->prefix.p, g.T + 1, nullptr, s);
+  }
+  c->launches += launch_step_advance((int*)c->d_step.p, s);
+}
+
+void do_generate(gstvd_ctx* c, int B, const gstvd_gen_params& gp, const int64_t* hist_ids, const int64_t* hist_seg, int Lh,
+                 int64_t* out_ids, float* out_scores, cudaStream_t s) {
+  check_ready(c);
+  if (c->dec_layers == 0) throw StateError("generate: encoder-only context");
+  if (c->cross_B != B) throw StateError(fmt("generate: cross K/V prefilled for %d images, asked for %d", c->cross_B, B));
+  const int T = gp.max_new_tokens;
+  if (T < 1 || T > c->T_max) throw InvalidArg("generate: max_new_tokens out of range");
+  if (!out_ids) throw InvalidArg("generate: out_ids is NULL");
+  int K = 1;
+  if (gp.mode == GSTVD_SELECT_BEAM) {
+    K = gp.num_beams;
+    if (K < 1 || K > c->K_max || 2 * K > kSelMax) throw InvalidArg("generate: num_beams out of range");
+    if (gp.ngram_blocking_size > 0) throw Unsupported("generate: n-gram blocking is only implemented for GSTVD_SELECT_SAMPLE");
+  } else if (gp.mode == GSTVD_SELECT_SAMPLE) {
+    if (gp.top_k < 1 || gp.top_k > GSTVD_MAX_TOP_K) throw Unsupported("generate: top_k must be in 1..16 (top_k = 0 / pure nucleus is not implemented)");
+    if (!(gp.temperature > 0.f)) throw InvalidArg("generate: temperature must be > 0");
+    if (gp.ngram_blocking_size > 0 && (!hist_ids || !hist_seg || Lh < 1 || Lh > c->Lt_max)) throw InvalidArg("generate: n-gram blocking needs hist_ids / hist_segments");
+  } else {
+    throw InvalidArg("generate: unknown mode");
+  }
+  const DecodeGeom g = make_geom(c, B, K, T);
+  // the sampling seed lives in device memory so that a captured graph can be replayed with a new seed
+  CUDA_CHECK(cudaMemcpyAsync(c->d_seed.p, &gp.seed, 8, cudaMemcpyHostToDevice, s));
+  if (gp.mode == GSTVD_SELECT_BEAM) c->launches += launch_beam_init(beam_buffers(c), B, K, T, 101, s);
+  else c->launches += launch_sample_init(B, T, 101, (int32_t*)c->seq.p, (int32_t*)c->cur_tokens.p, (int32_t*)c->prefix.p, T + 1, (int*)c->d_step.p, s);
+
+  const bool use_graph = !(c->cfg.flags & GSTVD_FLAG_NO_CUDA_GRAPH);
+  if (!use_graph) {
+    for (int t = 0; t < T; ++t) decode_step(c, g, gp, hist_ids, hist_seg, Lh, s);
+  } else {
+    GraphKey key;
+    std::memset(&key, 0, sizeof key);
+    key.B = B; key.K = K; key.mode = gp.mode; key.T = T; key.top_k = gp.top_k; key.ngram = gp.ngram_blocking_size; key.Lh = Lh;
+    key.temperature = gp.temperature; key.top_p = gp.top_p;
+    key.hist_ids = gp.ngram_blocking_size > 0 ? hist_ids : nullptr; key.hist_seg = gp.ngram_blocking_size > 0 ? hist_seg : nullptr;
+    // the cross cache geometry (Le) is part of the captured launch parameters
+    key.Lh = key.Lh * 1024 + c->cross_Le;
+    auto it = c->graphs.find(key);
+    if (it == c->graphs.end()) {
+      const int64_t before = c->launches;
+      cudaGraph_t graph;
+      CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      try {
+        decode_step(c, g, gp, hist_ids, hist_seg, Lh, s);
+      } catch (...) {
+        cudaGraph_t dead; cudaStreamEndCapture(s, &dead);
+        throw;
+      }
+      CUDA_CHECK(cudaStreamEndCapture(s, &graph));
+      cudaGraphExec_t exec;
+      CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+      CUDA_CHECK(cudaGraphDestroy(graph));
+      it = c->graphs.emplace(key, exec).first;
+      c->launches = before;                       // capture launches nothing
+    }
+    // kernels per replay = what one eager step would have launched
+    int64_t per_step;
+    {
+      const int per_layer = 11;
+      per_step = 1 + (int64_t)c->dec_layers * per_layer + 1 + (gp.mode == GSTVD_SELECT_BEAM ? 3 : (gp.ngram_blocking_size > 0 ? 3 : 2)) + 1;
+    }
+    for (int t = 0; t < T; ++t) { CUDA_CHECK(cudaGraphLaunch(it->second, s)); c->launches += per_step; }
+  }
+  if (gp.mode == GSTVD_SELECT_BEAM) c->launches += launch_beam_finalize(beam_buffers(c), B, K, T, 102, out_ids, out_scores, s);
+  else c->launches += launch_sample_finalize(B, T, 102, (const int32_t*)c->seq.p, out_ids, s);
+}
+
+void do_score(gstvd_ctx* c, int B, int L, int64_t* dec_ids, const float* dec_mask, const int64_t* labels, float* out_loss,
+              float* out_logits, cudaStream_t s) {
+  check_ready(c);
+  if (c->dec_layers == 0) throw StateError("score: encoder-only context");
+  if (c->cross_B != B) throw StateError(fmt("score: cross K/V prefilled for %d images, asked for %d", c->cross_B, B));
+  if (L < 1 || L > c->Ldec_max || L > c->cfg.max_position_embeddings) throw InvalidArg("score: L out of range");
+  if (!dec_ids) throw InvalidArg("score: dec_ids is NULL");
+  Exec X{c, s};
+  const int H = c->H, M = B * L, D = H / c->dec_heads, Le = c->cross_Le;
+  const int64_t* lab = labels;
+  if (!labels) {
+    c->launches += launch_shift_labels(B, L, dec_ids, (int64_t*)c->labels.p, 102, s);   // also [SEP] -> PAD in place (:53-57)
+    lab = (const int64_t*)c->labels.p;
+  }
+  c->launches += launch_embed_text(c->dtype, M, L, H, dec_ids, nullptr, nullptr, 0, c->word, c->pos, c->type, c->type_ext,
+                                   c->cfg.type_vocab_size, c->emb_ln.g, c->emb_ln.b, c->dh.p, s);
+  const int64_t per_image = (int64_t)2 * c->dec_heads * Le * D;
+  for (int l = 0; l < c->dec_layers; ++l) {
+    const DecLayer& Ly = c->d_layers[l];
+    X.gemm(c->dh.p, H, Ly.qkv, c->dqkv.p, 3 * H, M);
+    X.attention(c->dqkv.p, 3 * H, L, X.off(c->dqkv.p, H), X.off(c->dqkv.p, 2 * H), 3 * H, L, c->dctx.p, H, B, c->dec_heads, D, dec_mask,
+                -10000.0f, 1);
+    X.gemm(c->dctx.p, H, Ly.o, c->dtmp.p, H, M);
+    X.add_ln(c->dtmp.p, c->dh.p, Ly.ln_att, c->da.p, M);
+    X.gemm(c->da.p, H, Ly.cq, c->dqc.p, H, M);
+    {
+      AttnArgs a;
+      const char* kbase = (const char*)c->cross_cache.p + (size_t)l * B * per_image * c->esz;
+      a.q = c->dqc.p; a.q_bs = (int64_t)L * H; a.q_hs = D; a.q_rs = H;
+      a.k = kbase; a.k_bs = per_image; a.k_hs = (int64_t)Le * D; a.k_rs = D;
+      a.v = kbase + (size_t)c->dec_heads * Le * D * c->esz; a.v_bs = per_image; a.v_hs = a.k_hs; a.v_rs = D;
+      a.o = c->dctx.p; a.o_bs = (int64_t)L * H; a.o_hs = D; a.o_rs = H;
+      a.kmask = (const float*)c->fused_mask.p; a.kmask_bs = Le; a.neg = -1e9f; a.causal = 0;
+      a.B = B; a.H = c->dec_heads; a.Lq = L; a.Lk = Le; a.D = D; a.kv_batch_div = 1;
+      c->launches += launch_attention_generic(a, c->dtype, s);
+    }
+    X.gemm(c->dctx.p, H, Ly.co, c->dtmp.p, H, M);
+    X.add_ln(c->dtmp.p, c->da.p, Ly.ln_cross, c->db.p, M);
+    X.gemm(c->db.p, H, Ly.f1, c->dffn.p, c->dec_F, M, 1);
+    X.gemm(c->dffn.p, c->dec_F, Ly.f2, c->dtmp.p, H, M);
+    X.add_ln(c->dtmp.p, c->db.p, Ly.ln_out, c->dh.p, M);
+  }
+  float* lg = out_logits ? out_logits : (float*)c->logits.p;
+  const int64_t ldl = out_logits ? c->V : c->Vpad;
+  X.gemm(c->dh.p, H, c->lm_head, lg, ldl, M, 0, true);
+  if (out_loss) c->launches += launch_ce_loss(M, c->V, lg, ldl, lab, out_loss, s);
+}
+
+// scratch device buffer for the single-operator test entry points
+struct Scratch {
+  std::vector<void*> ptrs;
+  void* get(size_t bytes) { void* p; CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 16)); ptrs.push_back(p); return p; }
+  ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+};
+
+template <typename F>
+int guarded(gstvd_ctx* ctx, F&& f) {
+  int prev = -1;
+  cudaGetDevice(&prev);
+  int rc = GSTVD_OK;
+  try {
+    if (ctx) CUDA_CHECK(cudaSetDevice(ctx->device));
+    f();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA launch error: ") + cudaGetErrorString(e));
+  } catch (const InvalidArg& e) { rc = GSTVD_ERR_INVALID; g_last_error = e.what(); }
+  catch (const StateError& e) { rc = GSTVD_ERR_STATE; g_last_error = e.what(); }
+  catch (const Unsupported& e) { rc = GSTVD_ERR_UNSUPPORTED; g_last_error = e.what(); }
+  catch (const std::exception& e) {
+    rc = std::strstr(e.what(), "CUDA") ? GSTVD_ERR_CUDA : GSTVD_ERR_INVALID;
+    g_last_error = e.what();
+  }
+  if (rc != GSTVD_OK && ctx) ctx->last_error = g_last_error;
+  if (prev >= 0) cudaSetDevice(prev);
+  return rc;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+int gstvd_abi_version(void) { return GSTVD_ABI_VERSION; }
+
+const char* gstvd_last_error(const gstvd_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_last_error.c_str(); }
+
+int gstvd_create(const gstvd_config* cfg, int device, gstvd_ctx** out) {
+  if (!cfg || !out) { g_last_error = "gstvd_create: NULL argument"; return GSTVD_ERR_INVALID; }
+  *out = nullptr;
+  gstvd_ctx* c = nullptr;
+  int rc = guarded(nullptr, [&] {
+    if (cfg->abi_version != GSTVD_ABI_VERSION) throw InvalidArg("gstvd_create: abi_version mismatch");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw Unsupported("gstvd_create: no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) throw InvalidArg("gstvd_create: bad device index");
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) throw Unsupported(fmt("gstvd_create: device %d is sm_%d%d; this library only runs on sm_100 (B200)", device, prop.major, prop.minor));
+    CUDA_CHECK(cudaSetDevice(device));
+    const gstvd_config& g = *cfg;
+    if (g.compute_dtype != GSTVD_F32 && g.compute_dtype != GSTVD_BF16) throw InvalidArg("gstvd_create: compute_dtype");
+    if (g.num_connections < 0 || g.num_connections > GSTVD_MAX_CONNECTIONS) throw InvalidArg("gstvd_create: num_connections");
+    if (g.hidden_size % g.num_attention_heads || g.v_hidden_size % g.v_num_attention_heads || g.bi_hidden_size % g.bi_num_attention_heads)
+      throw InvalidArg("gstvd_create: hidden sizes must be divisible by head counts");
+    auto bad_dim = [](int n) { return n <= 0 || n % 8 != 0; };
+    if (bad_dim(g.hidden_size) || bad_dim(g.v_hidden_size) || bad_dim(g.bi_hidden_size) || bad_dim(g.intermediate_size) ||
+        bad_dim(g.v_intermediate_size) || bad_dim(g.v_feature_size))
+      throw InvalidArg("gstvd_create: feature dimensions must be positive multiples of 8");
+    if (g.hidden_size > 1024 || g.v_hidden_size > 1024) throw Unsupported("gstvd_create: hidden sizes above 1024 are not supported by the row kernels");
+    if (g.max_batch < 1 || g.max_text_len < 1 || g.max_regions < 1) throw InvalidArg("gstvd_create: capacities must be positive");
+    if (g.max_text_len + g.max_regions > 512) throw Unsupported("gstvd_create: at most 512 encoder positions");
+    c = new gstvd_ctx();
+    c->cfg = g; c->device = device; c->num_sms = prop.multiProcessorCount; c->dtype = g.compute_dtype; c->esz = g.compute_dtype == GSTVD_F32 ? 4 : 2;
+    c->H = g.hidden_size; c->Hv = g.v_hidden_size; c->Hb = g.bi_hidden_size; c->heads = g.num_attention_heads; c->heads_v = g.v_num_attention_heads;
+    c->heads_b = g.bi_num_attention_heads; c->F = g.intermediate_size; c->Fv = g.v_intermediate_size; c->V = g.vocab_size;
+    c->Vpad = (g.vocab_size + 7) & ~7;
+    c->Lt_max = g.max_text_len; c->Lv_max = g.max_regions; c->Le_max = g.max_text_len + g.max_regions; c->B_max = g.max_batch;
+    c->T_max = g.max_new_tokens > 0 ? g.max_new_tokens : 18; c->K_max = g.max_beams > 0 ? g.max_beams : 1;
+    c->Ldec_max = g.max_dec_len > 0 ? g.max_dec_len : 25;
+    if (c->Ldec_max < c->T_max) c->Ldec_max = c->T_max;
+    c->dec_layers = g.dec_num_hidden_layers; c->dec_heads = g.dec_num_attention_heads > 0 ? g.dec_num_attention_heads : 1;
+    c->dec_F = g.dec_intermediate_size;
+    if (c->dec_layers > 0) {
+      if (c->H % c->dec_heads) throw InvalidArg("gstvd_create: decoder heads");
+      const int D = c->H / c->dec_heads;
+      if (D != 64 && D != 128) throw Unsupported("gstvd_create: decoder head_dim must be 64 or 128");
+      if (c->T_max > 32 || c->K_max > 8) throw Unsupported("gstvd_create: at most 32 new tokens and 8 beams");
+      if (bad_dim(c->dec_F)) throw InvalidArg("gstvd_create: dec_intermediate_size");
+    }
+    if (c->dtype == kBF16) gemm_tc_init();
+    plan_weights(c);
+    alloc_workspace(c);
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
+    CUDA_CHECK(cudaDeviceSynchronize());
+  });
+  if (rc != GSTVD_OK) { if (c) gstvd_destroy(c); return rc; }
+  *out = c;
+  return GSTVD_OK;
+}
+
+void gstvd_destroy(gstvd_ctx* c) {
+  if (!c) return;
+  int prev = -1; cudaGetDevice(&prev);
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+  DevBuf* bufs[] = {&c->mat32, &c->mat16, &c->vec32, &c->xt, &c->yt, &c->xv, &c->yv, &c->qkv_t, &c->qkv_v, &c->ctx_t, &c->ctx_v, &c->tmp_t,
+                    &c->tmp_v, &c->ffn_t, &c->ffn_v, &c->feat_cast, &c->fused, &c->pool, &c->fused_mask, &c->dh, &c->da, &c->db, &c->dqkv,
+                    &c->dctx, &c->dtmp, &c->dffn, &c->dqc, &c->logits, &c->cross_cache, &c->self_cache, &c->labels, &c->sel_val, &c->sel_idx,
+                    &c->logz, &c->ban_tokens, &c->ban_count, &c->prefix, &c->seq, &c->beam_scores, &c->beam_tokens, &c->cur_tokens,
+                    &c->beam_idx, &c->beam_done, &c->hyp_score, &c->hyp_len, &c->hyp_tokens, &c->hyp_count, &c->hyp_worst, &c->d_step, &c->d_seed};
+  for (DevBuf* b : bufs) b->release();
+  if (c->ev_in) cudaEventDestroy(c->ev_in);
+  if (c->ev_out) cudaEventDestroy(c->ev_out);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  if (prev >= 0) cudaSetDevice(prev);
+}
+
+int gstvd_load_weight(gstvd_ctx* c, const char* name, const float* data, int64_t numel, void* stream) {
+  if (!c || !name || !data) { g_last_error = "gstvd_load_weight: NULL argument"; return GSTVD_ERR_INVALID; }
+  int result = 0;
+  int rc = guarded(c, [&] {
+    const std::string n = canonical_name(name);
+    auto it = c->slots.find(n);
+    if (it == c->slots.end()) {
+      if (is_ignored_key(n)) { result = 1; return; }
+      throw InvalidArg(std::string("gstvd_load_weight: unknown key '") + name + "'");
+    }
+    if (it->second.numel != numel) throw InvalidArg(fmt("gstvd_load_weight: '%s' has %lld elements, expected %lld", name, (long long)numel, (long long)it->second.numel));
+    CUDA_CHECK(cudaMemcpyAsync(it->second.dst, data, (size_t)numel * 4, cudaMemcpyDefault, (cudaStream_t)stream));
+    it->second.loaded = true;
+    c->finalized = false;
+  });
+  return rc != GSTVD_OK ? rc : result;
+}
+
+int gstvd_missing_weights(const gstvd_ctx* c) {
+  if (!c) return -1;
+  int n = 0;
+  for (auto& kv : c->slots) if (!kv.second.loaded) ++n;
+  return n;
+}
+
+int gstvd_finalize_weights(gstvd_ctx* c, void* stream) {
+  if (!c) { g_last_error = "gstvd_finalize_weights: NULL context"; return GSTVD_ERR_INVALID; }
+  return guarded(c, [&] {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c->dtype == kBF16) {
+      c->launches += launch_cast_f32_to(kBF16, (const float*)c->mat32.p, c->mat16.p, (int64_t)c->mat_elems, s);
+      assign_w16(c);
+    }
+    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    c->graphs.clear();
+    c->finalized = true;
+  });
+}
+
+int gstvd_encode(gstvd_ctx* c, int B, int Lt, int Lv, const int64_t* input_ids, const int64_t* token_type_ids, const float* attention_mask,
+                 const float* image_feat, const float* image_loc, const float* image_mask, float* out_t, float* out_v, float* out_fused,
+                 float* out_fused_mask, float* out_nsp, void* stream) {
+  if (!c) { g_last_error = "gstvd_encode: NULL context"; return GSTVD_ERR_INVALID; }
+  return guarded(c, [&] { do_encode(c, B, Lt, Lv, input_ids, token_type_ids, attention_mask, image_feat, image_loc, image_mask, out_t, out_v,
+                                    out_fused, out_fused_mask, out_nsp, (cudaStream_t)stream); });
+}
+
+int gstvd_prefill_cross(gstvd_ctx* c, int B, int Le, const float* enc_hidden, const float* enc_mask, void* stream) {
+  if (!c) { g_last_error = "gstvd_prefill_cross: NULL context"; return GSTVD_ERR_INVALID; }
+  return guarded(c, [&] { do_prefill(c, B, Le, enc_hidden, enc_mask, (cudaStream_t)stream); });
+}
+
+int gstvd_generate(gstvd_ctx* c, int B, const gstvd_gen_params* params, const int64_t* hist_ids, const int64_t* hist_segments, int Lh,
+                   int64_t* out_ids, float* out_scores, void* stream) {
+  if (!c || !params) { g_last_error = "gstvd_generate: NULL argument"; return GSTVD_ERR_INVALID; }
+  return guarded(c, [&] {
+    cudaStream_t user = (cudaStream_t)stream;
+    CUDA_CHECK(cudaEventRecord(c->ev_in, user));
+    CUDA_CHECK(cudaStreamWaitEvent(c->own_stream, c->ev_in, 0));
+    do_generate(c, B, *params, hist_ids, hist_segments, Lh, out_ids, out_scores, c->own_stream);
+    CUDA_CHECK(cudaEventRecord(c->ev_out, c->own_stream));
+    CUDA_CHECK(cudaStreamWaitEvent(user, c->ev_out, 0));
+  });
+}
+
+int gstvd_score(gstvd_ctx* c, int B, int L, int64_t* dec_ids, const float* dec_mask, const int64_t* labels, float* out_loss,
+                float* out_logits, void* stream) {
+  if (!c) { g_last_error = "gstvd_score: NULL context"; return GSTVD_ERR_INVALID; }
+  return guarded(c, [&] { do_score(c, B, L, dec_ids, dec_mask, labels, out_loss, out_logits, (cudaStream_t)stream); });
+}
+
+int gstvd_reorder_cache(gstvd_ctx* c, int B, int K, int len, const int32_t* beam_idx, void* stream) {
+  if (!c || !beam_idx) { g_last_error = "gstvd_reorder_cache: NULL argument"; return GSTVD_ERR_INVALID; }
+  return guarded(c, [&] {
+    if (c->dec_layers == 0) throw StateError("reorder_cache: encoder-only context");
+    if (B < 1 || B > c->B_max || K < 1 || K > c->K_max || len < 0 || len > c->T_max) throw InvalidArg("reorder_cache: shape out of range");
+    DecodeGeom g = make_geom(c, B, K, c->T_max);
+    c->launches += launch_reorder_cache(c->dtype, g, c->self_cache.p, beam_idx, nullptr, len, nullptr, (cudaStream_t)stream);
+  });
+}
+
+int gstvd_splice(gstvd_ctx* c, int B, int Lt, int Lu, int64_t* enc_input_ids, int64_t* enc_segments, float* attention_mask,
+                 int32_t* enc_len, const int64_t* utt, int segment_value, int strip_sep, int32_t* abnormal, void* stream) {
+  if (!c || !enc_input_ids || !enc_len || !utt) { g_last_error = "gstvd_splice: NULL argument"; return GSTVD_ERR_INVALID; }
+  return guarded(c, [&] {
+    c->launches += launch_splice(B, Lt, Lu, enc_input_ids, enc_segments, attention_mask, enc_len, utt, segment_value, strip_sep, abnormal, 102,
+                                 (cudaStream_t)stream);
+  });
+}
+
+int64_t gstvd_launch_count(const gstvd_ctx* c) { return c ? c->launches : -1; }
+
+// ---- single operators ------------------------------------------------------------------------------------------
+int gstvd_op_linear(gstvd_ctx* c, int dtype, int M, int N, int K, const float* a, const float* w, const float* bias, int act, float* out,
+                    void* stream) {
+  if (!c) return GSTVD_ERR_INVALID;
+  return guarded(c, [&] {
+    cudaStream_t s = (cudaStream_t)stream;
+    GemmArgs g;
+    g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldc = N; g.bias = bias; g.act = act; g.C = out; g.out_f32 = 1;
+    if (dtype == kF32) {
+      g.A = a; g.W = w;
+      c->launches += launch_gemm_simt(g, kF32, s);
+    } else {
+      Scratch sc;
+      void* a16 = sc.get((size_t)M * K * 2); void* w16 = sc.get((size_t)N * K * 2);
+      c->launches += launch_cast_f32_to(kBF16, a, a16, (int64_t)M * K, s);
+      c->launches += launch_cast_f32_to(kBF16, w, w16, (int64_t)N * K, s);
+      g.A = a16; g.W = w16;
+      gemm_tc_init();
+      if (c->cfg.flags & GSTVD_FLAG_DEBUG_SIMT_GEMM) c->launches += launch_gemm_simt(g, kBF16, s);
+      else c->launches += launch_gemm_tc(g, c->num_sms, s);
+      CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+  });
+}
+
+int gstvd_op_add_layernorm(gstvd_ctx* c, int dtype, int rows, int width, const float* x, const float* residual, const float* gamma,
+                           const float* beta, float* y, void* stream) {
+  if (!c) return GSTVD_ERR_INVALID;
+  return guarded(c, [&] {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == kF32) {
+      c->launches += launch_add_layernorm(kF32, rows, width, x, width, residual, width, gamma, beta, y, width, s);
+    } else {
+      Scratch sc;
+      const int64_t n = (int64_t)rows * width;
+      void* x16 = sc.get(n * 2); void* r16 = residual ? sc.get(n * 2) : nullptr; void* y16 = sc.get(n * 2);
+      c->launches += launch_cast_f32_to(kBF16, x, x16, n, s);
+      if (residual) c->launches += launch_cast_f32_to(kBF16, residual, r16, n, s);
+      c->launches += launch_add_layernorm(kBF16, rows, width, x16, width, r16, width, gamma, beta, y16, width, s);
+      c->launches += launch_cast_to_f32(kBF16, y16, y, n, s);
+      CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+  });
+}
+
+int gstvd_op_attention(gstvd_ctx* c, int dtype, int B, int H, int Lq, int Lk, int D, const float* q, const float* k, const float* v,
+                       const float* mask, float neg, int causal, float* out, void* stream) {
+  if (!c) return GSTVD_ERR_INVALID;
+  return guarded(c, [&] {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t W = (int64_t)H * D;
+    AttnArgs a;
+    a.q_bs = Lq * W; a.q_hs = D; a.q_rs = W; a.k_bs = Lk * W; a.k_hs = D; a.k_rs = W; a.v_bs = Lk * W; a.v_hs = D; a.v_rs = W;
+    a.o_bs = Lq * W; a.o_hs = D; a.o_rs = W; a.kmask = mask; a.kmask_bs = Lk; a.neg = neg; a.causal = causal;
+    a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.D = D;
+    if (dtype == kF32) {
+      a.q = q; a.k = k; a.v = v; a.o = out;
+      c->launches += launch_attention_generic(a, kF32, s);
+    } else {
+      Scratch sc;
+      const int64_t nq = (int64_t)B * Lq * W, nk = (int64_t)B * Lk * W;
+      void* q16 = sc.get(nq * 2); void* k16 = sc.get(nk * 2); void* v16 = sc.get(nk * 2); void* o16 = sc.get(nq * 2);
+      c->launches += launch_cast_f32_to(kBF16, q, q16, nq, s);
+      c->launches += launch_cast_f32_to(kBF16, k, k16, nk, s);
+      c->launches += launch_cast_f32_to(kBF16, v, v16, nk, s);
+      a.q = q16; a.k = k16; a.v = v16; a.o = o16;
+      c->launches += launch_attention_generic(a, kBF16, s);
+      c->launches += launch_cast_to_f32(kBF16, o16, out, nq, s);
+      CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+  });
+}
+
+int gstvd_op_beam_begin(gstvd_ctx* c, int B, int K, int max_new, void* stream) {
+  if (!c) return GSTVD_ERR_INVALID;
+  return guarded(c, [&] {
+    if (c->dec_layers == 0) throw StateError("beam ops need a decoder context");
+    if (B < 1 || B > c->B_max || K < 1 || K > c->K_max || max_new < 1 || max_new > c->T_max) throw InvalidArg("beam_begin: shape out of range");
+    c->op_B = B; c->op_K = K; c->op_T = max_new;
+    c->launches += launch_beam_init(beam_buffers(c), B, K, max_new, 101, (cudaStream_t)stream);
+  });
+}
+
+int gstvd_op_beam_step(gstvd_ctx* c, const float* logits, int64_t ldl, int32_t* beam_idx, int32_t* next_tokens, float* next_scores,
+                       void* stream) {
+  if (!c || !logits) return GSTVD_ERR_INVALID;
+  return guarded(c, [&] {
+    if (c->op_B == 0) throw StateError("beam_step before beam_begin");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = c->op_B, K = c->op_K, T = c->op_T, nsel = 2 * K;
+    c->launches += launch_row_select(B * K, c->V, logits, ldl, 0, (const float*)c->beam_scores.p, 1.f, nullptr, nullptr, 0, nsel,
+                                     (float*)c->sel_val.p, (int32_t*)c->sel_idx.p, nullptr, s);
+    c->launches += launch_beam_step(beam_buffers(c), B, K, T, c->V, nsel, (const float*)c->sel_val.p, (const int32_t*)c->sel_idx.p, 102,
+                                    beam_idx, next_tokens, next_scores, s);
+    c->launches += launch_step_advance((int*)c->d_step.p, s);
+  });
+}
+
+int gstvd_op_beam_end(gstvd_ctx* c, int64_t* out_ids, float* out_scores, void* stream) {
+  if (!c || !out_ids) return GSTVD_ERR_INVALID;
+  return guarded(c, [&] {
+    if (c->op_B == 0) throw StateError("beam_end before beam_begin");
+    c->launches += launch_beam_finalize(beam_buffers(c), c->op_B, c->op_K, c->op_T, 102, out_ids, out_scores, (cudaStream_t)stream);
+    c->op_B = 0;
+  });
+}
+
+int gstvd_op_sample(gstvd_ctx* c, int rows, const float* logits, int64_t ldl, const gstvd_gen_params* gp, const int64_t* hist_ids,
+                    const int64_t* hist_segments, int Lh, const int64_t* prefix, int prefix_len, int step, int32_t* out_tokens, void* stream) {
+  if (!c || !logits || !gp || !out_tokens) return GSTVD_ERR_INVALID;
+  return guarded(c, [&] {
+    if (c->dec_layers == 0) throw StateError("sample op needs a decoder context");
+    if (rows < 1 || rows > c->B_max) throw InvalidArg("op_sample: rows out of range");
+    if (gp->top_k < 1 || gp->top_k > GSTVD_MAX_TOP_K) throw Unsupported("op_sample: top_k must be in 1..16");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int T = c->T_max;
+    CUDA_CHECK(cudaMemcpyAsync(c->d_step.p, &step, 4, cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(c->d_seed.p, &gp->seed, 8, cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    const int32_t* bt = nullptr; const int32_t* bc = nullptr;
+    if (gp->ngram_blocking_size > 0) {
+      if (!hist_ids || !hist_segments || !prefix || prefix_len != step + 1) throw InvalidArg("op_sample: n-gram blocking needs history and a prefix of step+1 tokens");
+      CUDA_CHECK(cudaMemsetAsync(c->prefix.p, 0, c->prefix.bytes, s));
+      c->launches += launch_build_prefix_from_ids(rows, prefix_len, prefix, (int32_t*)c->prefix.p, T + 1, 102, s);
+      c->launches += launch_ngram_ban(rows, Lh, hist_ids, hist_segments, (const int32_t*)c->prefix.p, T + 1, (const int*)c->d_step.p,
+                                      gp->ngram_blocking_size, (int32_t*)c->ban_tokens.p, (int32_t*)c->ban_count.p, Lh, s);
+      bt = (const int32_t*)c->ban_tokens.p; bc = (const int32_t*)c->ban_count.p;
+    }
+    c->launches += launch_row_select(rows, c->V, logits, ldl, 1, nullptr, gp->temperature, bt, bc, Lh, kSelMax, (float*)c->sel_val.p,
+                                     (int32_t*)c->sel_idx.p, nullptr, s);
+    c->launches += launch_sample_step(rows, T, kSelMax, (const float*)c->sel_val.p, (const int32_t*)c->sel_idx.p, gp->top_k, gp->top_p, gp->seed, nullptr,
+                                      (const int*)c->d_step.p, 102, (int32_t*)c->seq.p, (int32_t*)c->cur_tokens.p, (int32_t*)c->prefix.p, T + 1,
+                                      out_tokens, s);
+  });
+}
+
+}  // extern "C"

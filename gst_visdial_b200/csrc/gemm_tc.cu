@@ -1,0 +1,410 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = act(A[M,K] * W[N,K]^T + bias), bf16 operands, fp32 accumulate.
+//
+// Replaces every nn.Linear on the hot path when the compute dtype is bf16: the q/k/v, output and FFN projections of
+// the text / image / connection layers (models/vilbert_dialog.py:366-368,412,437,454,493-495,539,564,581,624-633,
+// 718,725,753-757), the image embedding (:1415), VLFusion (models/visual_dialog_model.py:127-128), the decoder
+// layers and the LM head (models/visual_dialog_decoder.py:300-311,329-339).
+//
+// Design (one CTA per SM, persistent over output tiles, warp specialised):
+//   warp 0      : TMA producer  - cp.async.bulk.tensor.2d loads of the A (128 x 64) and W (BN x 64) k-blocks into a
+//                 STAGES-deep shared-memory ring (128-byte swizzle), completion on mbarriers
+//   warp 1      : MMA issuer    - one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per k-block
+//                 into one of two TMEM accumulator stages; tcgen05.commit releases ring slots / signals the epilogue
+//   warps 2..9  : epilogue      - tcgen05.ld (32 lanes x 32 columns per warp), + bias, erf-GELU, convert, 128-bit stores.
+//                 Two accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+// Both operands are K-major ("TN"), which is the layout of activations [rows, features] and nn.Linear weights
+// [out, in], so no transposes are ever materialised.  TMA zero-fills out-of-range rows / k, so M, N, K need not be
+// multiples of the tile (K % 8 == 0 for the 16-byte stride rule).
+#include <cuda.h>
+
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gstvd {
+
+namespace {
+
+constexpr int BM = 128;          // rows per tile  (UMMA M)
+constexpr int BK = 64;           // k per stage: 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (2 + kEpiWarps) * 32;
+constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;   // 4 s: far beyond any legitimate wait
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  unsigned long long t0 = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && (++spins & 1023u) == 0) {         // a protocol bug must fail the launch, never hang the GPU
+      unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kWaitTimeoutNs) __trap();
+    }
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+// K-major operand tile in shared memory, 128-byte swizzle: rows of 64 bf16 (128 B); 8-row groups are 1024 B apart.
+// Descriptor fields (PTX ISA "tcgen05 shared memory descriptor"): start address >> 4 [0,14), leading byte offset >> 4
+// [16,30) (unused for swizzled K-major, set to 1), stride byte offset >> 4 [32,46) = 1024 >> 4, version 1 at [46,48),
+// layout type SWIZZLE_128B = 2 at [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor for kind::f16: D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9 / 10-12 = 1), both K-major
+// (bits 15, 16 = 0), N >> 3 at [17,23), M >> 4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives lane (base_lane + i), columns c..c+31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN> struct TileCfg {
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // power of two for BN in {16,32,64,128,256}
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kBarBytes + 1024;   // +1024: manual alignment slack
+};
+
+template <typename OutT>
+__device__ __forceinline__ void store_chunk(const GemmArgs& p, int row, int col0, uint32_t (&acc)[32]) {
+  // acc: 32 consecutive output columns of `row`, raw fp32 accumulators
+  int64_t idx;
+  if (p.hm_D > 0) {
+    int b = row / p.hm_L, pos = row - b * p.hm_L;
+    int g = col0 / p.hm_D, d = col0 - g * p.hm_D;
+    int layer = g / p.hm_G, r = g - layer * p.hm_G;
+    idx = ((((int64_t)layer * p.hm_B + b) * p.hm_G + r) * p.hm_L + pos) * p.hm_D + d;
+  } else {
+    idx = (int64_t)row * p.ldc + col0;
+  }
+  OutT* out = reinterpret_cast<OutT*>(p.C) + idx;
+  const bool full = (col0 + 32 <= p.N);
+  const bool vec_ok = full && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const bool bias_vec = p.bias != nullptr && full && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0);
+#pragma unroll
+  for (int g8 = 0; g8 < 4; ++g8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g8 * 8 + j]);
+    if (p.bias) {
+      if (bias_vec) {
+        float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g8 * 8));
+        float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g8 * 8 + 4));
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          int c = col0 + g8 * 8 + j;
+          if (c < p.N) v[j] += __ldg(p.bias + c);
+        }
+      }
+    }
+    if (p.act == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+    }
+    if (vec_ok) {
+      Vec8<OutT>::store(out + g8 * 8, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int c = col0 + g8 * 8 + j;
+        if (c < p.N) out[g8 * 8 + j] = from_f32<OutT>(v[j]);
+      }
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmArgs p) {
+  using Cfg = TileCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                 // 128B-swizzle atoms need 1024-byte alignment
+  const uint32_t a_base = base;
+  const uint32_t b_base = base + kStages * Cfg::kABytes;
+  const uint32_t bar_base = b_base + kStages * Cfg::kBBytes;
+  // barrier layout: full[kStages] | empty[kStages] | tmem_full[2] | tmem_empty[2] | tmem base address (u32)
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  uint8_t* smem_gen = smem_raw + (base - raw);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps * 32); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::kABytes + Cfg::kBBytes);
+          tma_load_2d(a_base + stage * Cfg::kABytes, &tm_a, kb * BK, m_blk * BM, full_bar(stage));
+          tma_load_2d(b_base + stage * Cfg::kBBytes, &tm_b, kb * BK, n_blk * BN, full_bar(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int stage = 0; uint32_t phase = 0; int iter = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+        const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);      // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);         // TMA bytes have landed
+          tc_fence_after();
+          const uint64_t a_desc = make_smem_desc(a_base + stage * Cfg::kABytes);
+          const uint64_t b_desc = make_smem_desc(b_base + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));             // frees the smem slot when these MMAs retire
+          if (kb == num_kb - 1) umma_commit(tfull_bar(as));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue ----------------
+    const int e = warp - 2;
+    const int quad = warp & 3;                        // TMEM lane quadrant this warp may access
+    const int half = e >> 2;                          // two warps per quadrant split the columns
+    constexpr int kColsPerHalf = BN >= 64 ? BN / 2 : BN;
+    const int c_begin = (BN >= 64) ? half * kColsPerHalf : 0;
+    const int c_end = (BN >= 64) ? c_begin + kColsPerHalf : (half == 0 ? BN : 0);
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+      const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int row = m_blk * BM + quad * 32 + lane;
+      for (int c = c_begin; c < c_end; c += 32) {
+        const int col0 = n_blk * BN + c;
+        if (col0 >= p.N) break;                       // warp-uniform
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + c, acc);
+        if (row < p.M) {
+          if (p.out_f32) store_chunk<float>(p, row, col0, acc);
+          else store_chunk<bf16>(p, row, col0, acc);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::once_flag g_once;
+
+struct MapKey {
+  const void* ptr; int64_t rows, cols, ld; int box_rows;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h = h * 1000003u ^ static_cast<size_t>(k.rows); h = h * 1000003u ^ static_cast<size_t>(k.cols);
+    h = h * 1000003u ^ static_cast<size_t>(k.ld); h = h * 1000003u ^ static_cast<size_t>(k.box_rows);
+    return h;
+  }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// 2-D bf16 tensor [rows, cols] with row stride ld (elements); box = 64 columns x box_rows rows, 128-byte swizzle.
+const CUtensorMap& get_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  MapKey key{ptr, rows, cols, ld, box_rows};
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) return it->second;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0)
+    throw std::runtime_error("gemm_tc: operand must be 16-byte aligned with a row stride that is a multiple of 8 elements");
+  CUtensorMap m;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld * 2)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  if (g_maps.size() > 4096) g_maps.clear();
+  return g_maps.emplace(key, m).first->second;
+}
+
+template <int BN>
+void launch_cfg(const GemmArgs& a, int num_sms, cudaStream_t stream) {
+  using Cfg = TileCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("gemm_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const CUtensorMap& ma = get_map(a.A, a.M, a.K, a.lda, BM);
+  const CUtensorMap& mb = get_map(a.W, a.N, a.K, a.ldw, BN);
+  const int tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_tc_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ma, mb, a);
+}
+
+}  // namespace
+
+void gemm_tc_init() {
+  std::call_once(g_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr)
+      throw std::runtime_error("gemm_tc: cannot resolve cuTensorMapEncodeTiled");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  });
+}
+
+int launch_gemm_tc(const GemmArgs& a, int num_sms, cudaStream_t stream) {
+  if (a.M <= 0 || a.N <= 0) return 0;
+  if (a.K % 8 != 0) throw std::runtime_error("gemm_tc: K must be a multiple of 8");
+  if (a.hm_D > 0 && (a.hm_D % 32 != 0)) throw std::runtime_error("gemm_tc: head-major scatter needs head_dim % 32 == 0");
+  gemm_tc_init();
+  const int tiles_m = (a.M + BM - 1) / BM;
+  // largest N tile that still gives every SM a tile; small problems fall through to the narrowest tile
+  int bn = 32;
+  const int cand[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    if (a.N >= cand[i] && tiles_m * ((a.N + cand[i] - 1) / cand[i]) >= num_sms) { bn = cand[i]; break; }
+  }
+  switch (bn) {
+    case 256: launch_cfg<256>(a, num_sms, stream); break;
+    case 128: launch_cfg<128>(a, num_sms, stream); break;
+    case 64: launch_cfg<64>(a, num_sms, stream); break;
+    default: launch_cfg<32>(a, num_sms, stream); break;
+  }
+  return 1;
+}
+
+}  // namespace gstvd

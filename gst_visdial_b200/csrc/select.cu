@@ -1,0 +1,510 @@
+// Token selection: log-softmax + top-k per row, beam-search bookkeeping, top-k/top-p sampling, n-gram blocking,
+// cross-entropy, and the dialog-history splice.  Integer / index results are bit-exact against oracle/beam.py and
+// the reference's utils/decoding_utils.py; see the arithmetic contract at the top of oracle/beam.py.
+//
+//   row_select     : replaces torch.topk + masked fill (utils/decoding_utils.py:17-21) and, for beams, the
+//                    log_softmax + top-2K of HF beam_search (absent from the reference; contract in oracle/beam.py)
+//   beam_step/...  : BeamSearchScorer.process / finalize + BeamHypotheses (transformers 4.16.2 semantics)
+//   ngram_ban      : batch_ngram_blocking (utils/decoding_utils.py:38-78) without host round trips
+//   sample_step    : softmax + multinomial (models/visual_dialog_model.py:106-107), counter-based RNG
+//   ce_loss        : CrossEntropyLoss(ignore_index=0, reduction='none') (models/visual_dialog_decoder.py:70-77)
+//   splice         : generate.py:145-160 and :214-228
+#include <stdexcept>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gstvd {
+
+namespace {
+
+constexpr int kSelThreads = 1024;
+constexpr int kSlots = 32;                 // vocab <= 32768
+constexpr int kHypMaxT = 32;
+
+struct Cand { float v; int i; };
+__device__ __forceinline__ bool better(float av, int ai, float bv, int bi) { return av > bv || (av == bv && ai < bi); }
+
+__global__ void __launch_bounds__(kSelThreads)
+row_select_kernel(int V, const float* __restrict__ logits, int64_t ldl, int mode, const float* __restrict__ row_bias,
+                  float temperature, const int32_t* __restrict__ ban_tokens, const int32_t* __restrict__ ban_count,
+                  int ban_stride, int nsel, float* __restrict__ sel_val, int32_t* __restrict__ sel_idx, float* __restrict__ logz) {
+  __shared__ float s_f[32];
+  __shared__ double s_d[32];
+  __shared__ int s_i[32];
+  __shared__ int s_bcast_i;
+  const int row = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* __restrict__ x = logits + (int64_t)row * ldl;
+  float v[kSlots];
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) {
+    const int idx = tid + s * kSelThreads;
+    v[s] = (idx < V) ? x[idx] : -INFINITY;
+  }
+  float lz = 0.f;
+  if (mode == 0 || logz != nullptr) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) m = fmaxf(m, v[s]);
+    m = warp_max(m);
+    if (lane == 0) s_f[warp] = m;
+    __syncthreads();
+    m = s_f[lane];
+    m = warp_max(m);
+    __syncthreads();
+    double acc = 0.0;
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s)
+      if (tid + s * kSelThreads < V) acc += exp((double)v[s] - (double)m);
+    acc = warp_sum(acc);
+    if (lane == 0) s_d[warp] = acc;
+    __syncthreads();
+    acc = s_d[lane];
+    acc = warp_sum(acc);
+    __syncthreads();
+    lz = (float)((double)m + log(acc));
+    if (logz != nullptr && tid == 0) logz[row] = lz;
+  }
+  if (mode == 0) {
+    const float bias = row_bias ? row_bias[row] : 0.f;
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s)
+      if (tid + s * kSelThreads < V) v[s] = __fadd_rn(__fsub_rn(v[s], lz), bias);
+  } else {
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s)
+      if (tid + s * kSelThreads < V) v[s] = __fdiv_rn(v[s], temperature);
+    const int nb = ban_count ? ban_count[row] : 0;
+    for (int j = 0; j < nb; ++j) {
+      const int w = ban_tokens[(int64_t)row * ban_stride + j];
+      if ((w % kSelThreads) == tid) {
+        const int slot = w / kSelThreads;
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s)
+          if (s == slot) v[s] = -INFINITY;
+      }
+    }
+  }
+  // iterative arg-max; ties resolved towards the lower index.  Each thread caches the best of its own slots and
+  // only the owner of the previous winner rescans.
+  float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) {
+    const int idx = tid + s * kSelThreads;
+    if (idx < V && v[s] > -INFINITY && better(v[s], idx, bv, bi)) { bv = v[s]; bi = idx; }
+  }
+  for (int r = 0; r < nsel; ++r) {
+    float cv = bv; int ci = bi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
+      if (better(ov, oi, cv, ci)) { cv = ov; ci = oi; }
+    }
+    if (lane == 0) { s_f[warp] = cv; s_i[warp] = ci; }
+    __syncthreads();
+    if (warp == 0) {
+      cv = s_f[lane]; ci = s_i[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
+        if (better(ov, oi, cv, ci)) { cv = ov; ci = oi; }
+      }
+      if (lane == 0) {
+        s_bcast_i = ci;
+        sel_val[(int64_t)row * nsel + r] = cv;
+        sel_idx[(int64_t)row * nsel + r] = (ci == 0x7fffffff) ? 0 : ci;
+      }
+    }
+    __syncthreads();
+    const int wi = s_bcast_i;
+    if (wi != 0x7fffffff && (wi % kSelThreads) == tid) {
+      const int slot = wi / kSelThreads;
+      bv = -INFINITY; bi = 0x7fffffff;
+#pragma unroll
+      for (int s = 0; s < kSlots; ++s) {
+        if (s == slot) v[s] = -INFINITY;
+        const int idx = tid + s * kSelThreads;
+        if (idx < V && v[s] > -INFINITY && better(v[s], idx, bv, bi)) { bv = v[s]; bi = idx; }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void beam_init_kernel(BeamBuffers bb, int B, int K, int T, int start_token) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *bb.d_step = 0;
+  if (i < B) { bb.done[i] = 0; bb.hyp_count[i] = 0; bb.hyp_worst[i] = 1e9; }
+  if (i < B * K) {
+    bb.beam_scores[i] = (i % K == 0) ? 0.f : -1e9f;
+    bb.cur_tokens[i] = start_token;
+    bb.beam_idx[i] = i % K;
+  }
+  for (int j = i; j < 2 * B * K * T; j += gridDim.x * blockDim.x) bb.tokens[j] = 0;
+}
+
+// BeamHypotheses.add (transformers 4.16.2): slots are kept in insertion order, capacity K (+1 transient)
+__device__ void hyp_add(const BeamBuffers& bb, int b, int K, int T, const int32_t* toks, int ntok, float sum_logprobs, int length) {
+  const double score = (double)sum_logprobs / (double)length;
+  const int HK = K + 1;
+  double* hs = bb.hyp_score + (int64_t)b * HK;
+  int32_t* hl = bb.hyp_len + (int64_t)b * HK;
+  int32_t* ht = bb.hyp_tokens + (int64_t)b * HK * T;
+  int cnt = bb.hyp_count[b];
+  if (cnt < K || score > bb.hyp_worst[b]) {
+    hs[cnt] = score; hl[cnt] = ntok;
+    for (int j = 0; j < T; ++j) ht[cnt * T + j] = (j < ntok) ? toks[j] : 0;
+    ++cnt;
+    if (cnt > K) {
+      // sorted by (score, insertion index): drop the first, worst = score of the second
+      int lo = 0;
+      for (int i = 1; i < cnt; ++i) if (hs[i] < hs[lo]) lo = i;
+      double second = 1e300;
+      for (int i = 0; i < cnt; ++i) if (i != lo && hs[i] < second) second = hs[i];
+      for (int i = lo; i + 1 < cnt; ++i) {
+        hs[i] = hs[i + 1]; hl[i] = hl[i + 1];
+        for (int j = 0; j < T; ++j) ht[i * T + j] = ht[(i + 1) * T + j];
+      }
+      --cnt;
+      bb.hyp_worst[b] = second;
+    } else {
+      bb.hyp_worst[b] = score < bb.hyp_worst[b] ? score : bb.hyp_worst[b];
+    }
+    bb.hyp_count[b] = cnt;
+  }
+}
+
+__global__ void beam_step_kernel(BeamBuffers bb, int B, int K, int T, int V, int nsel, const float* __restrict__ sel_val,
+                                 const int32_t* __restrict__ sel_idx, int eos, int32_t* out_beam_idx, int32_t* out_tokens,
+                                 float* out_scores) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int t = *bb.d_step;
+  const int cur_len = t + 1;
+  const int32_t* src = bb.tokens + (int64_t)(t & 1) * B * K * T + (int64_t)b * K * T;
+  int32_t* dst = bb.tokens + (int64_t)((t + 1) & 1) * B * K * T + (int64_t)b * K * T;
+  float nb_s[8]; int nb_tok[8], nb_par[8];
+  for (int k = 0; k < K; ++k) { nb_s[k] = 0.f; nb_tok[k] = 0; nb_par[k] = 0; }
+  if (!bb.done[b]) {
+    int head[8];
+    for (int k = 0; k < K; ++k) head[k] = 0;
+    int n = 0;
+    float best_sum = 0.f;
+    for (int rank = 0; rank < 2 * K; ++rank) {
+      // next candidate of the K-way merge, ordered by (score desc, beam*V + token asc)
+      int bk = -1; float bv = 0.f; int bt = 0;
+      for (int k = 0; k < K; ++k) {
+        if (head[k] >= nsel) continue;
+        const float v = sel_val[((int64_t)b * K + k) * nsel + head[k]];
+        const int tk = sel_idx[((int64_t)b * K + k) * nsel + head[k]];
+        if (bk < 0 || v > bv) { bk = k; bv = v; bt = tk; }     // equal score: the lower beam (lower flat index) stays
+      }
+      ++head[bk];
+      if (rank == 0) best_sum = bv;
+      if (bt == eos) {
+        if (rank >= K) continue;
+        hyp_add(bb, b, K, T, src + (int64_t)bk * T, t, bv, cur_len);
+      } else {
+        nb_s[n] = bv; nb_tok[n] = bt; nb_par[n] = bk; ++n;
+      }
+      if (n == K) break;
+    }
+    if (bb.hyp_count[b] >= K) {
+      const double cur = (double)best_sum / (double)cur_len;
+      if (bb.hyp_worst[b] >= cur) bb.done[b] = 1;
+    }
+  }
+  for (int k = 0; k < K; ++k) {
+    for (int j = 0; j < T; ++j) dst[k * T + j] = src[nb_par[k] * T + j];
+    if (t < T) dst[k * T + t] = nb_tok[k];
+    bb.beam_scores[b * K + k] = nb_s[k];
+    bb.cur_tokens[b * K + k] = nb_tok[k];
+    bb.beam_idx[b * K + k] = nb_par[k];
+    if (out_beam_idx) out_beam_idx[b * K + k] = nb_par[k];
+    if (out_tokens) out_tokens[b * K + k] = nb_tok[k];
+    if (out_scores) out_scores[b * K + k] = nb_s[k];
+  }
+}
+
+__global__ void beam_finalize_kernel(BeamBuffers bb, int B, int K, int T, int eos, int64_t* out_ids, float* out_scores) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int t = *bb.d_step;                     // steps executed
+  const int HK = K + 1;
+  if (!bb.done[b]) {
+    const int32_t* cur = bb.tokens + (int64_t)(t & 1) * B * K * T + (int64_t)b * K * T;
+    for (int k = 0; k < K; ++k) hyp_add(bb, b, K, T, cur + (int64_t)k * T, t, bb.beam_scores[b * K + k], t + 1);
+  }
+  const double* hs = bb.hyp_score + (int64_t)b * HK;
+  const int cnt = bb.hyp_count[b];
+  int best = 0;
+  for (int i = 1; i < cnt; ++i) if (hs[i] >= hs[best]) best = i;   // stable ascending sort, take the last
+  const int len = bb.hyp_len[(int64_t)b * HK + best];
+  const int32_t* ht = bb.hyp_tokens + ((int64_t)b * HK + best) * T;
+  for (int j = 0; j < T; ++j) out_ids[(int64_t)b * T + j] = (j < len) ? ht[j] : (j == len ? eos : 0);
+  if (out_scores) out_scores[b] = (float)hs[best];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_special(int64_t t) { return t == 0 || (t >= 100 && t <= 103); }
+
+__global__ void __launch_bounds__(256)
+ngram_ban_kernel(int Lh, const int64_t* __restrict__ hist_ids, const int64_t* __restrict__ hist_seg,
+                 const int32_t* __restrict__ prefix, int prefix_stride, const int* __restrict__ d_step, int n,
+                 int32_t* __restrict__ ban_tokens, int32_t* __restrict__ ban_count, int ban_stride) {
+  __shared__ int cnt;
+  const int row = blockIdx.x;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  const int cur_len = *d_step + 1;
+  const int start = cur_len + 1 - n;
+  if (start >= 0) {                                      // a shorter key can never equal an (n-1)-gram
+    const int64_t* ids = hist_ids + (int64_t)row * Lh;
+    const int64_t* seg = hist_seg + (int64_t)row * Lh;
+    const int32_t* key = prefix + (int64_t)row * prefix_stride + start;
+    for (int p = threadIdx.x; p + n <= Lh; p += blockDim.x) {
+      bool ok = true;
+      for (int j = 0; j < n && ok; ++j) {
+        const int64_t tk = (seg[p + j] == 0) ? ids[p + j] : 0;   // question history = ids * (segments == 0)
+        if (is_special(tk)) ok = false;
+        else if (j < n - 1 && tk != (int64_t)key[j]) ok = false;
+      }
+      if (ok) {
+        const int slot = atomicAdd(&cnt, 1);
+        if (slot < ban_stride) ban_tokens[(int64_t)row * ban_stride + slot] = (int32_t)ids[p + n - 1];
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) ban_count[row] = cnt < ban_stride ? cnt : ban_stride;
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void sample_init_kernel(int rows, int T, int start_token, int32_t* seq, int32_t* cur_tokens, int32_t* prefix,
+                                   int prefix_stride, int* d_step) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *d_step = 0;
+  if (i < rows) {
+    cur_tokens[i] = start_token;
+    for (int j = 0; j < T; ++j) seq[(int64_t)i * T + j] = 0;
+    for (int j = 0; j < prefix_stride; ++j) prefix[(int64_t)i * prefix_stride + j] = 0;
+    prefix[(int64_t)i * prefix_stride] = start_token;
+  }
+}
+
+__global__ void sample_step_kernel(int rows, int T, int nsel, const float* __restrict__ sel_val, const int32_t* __restrict__ sel_idx,
+                                   int top_k, float top_p, uint64_t seed, const uint64_t* __restrict__ d_seed,
+                                   const int* __restrict__ d_step, int eos, int32_t* seq, int32_t* cur_tokens, int32_t* prefix, int prefix_stride, int32_t* out_tokens) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const int step = *d_step;
+  const float* v = sel_val + (int64_t)row * nsel;
+  const int32_t* ix = sel_idx + (int64_t)row * nsel;
+  // keep everything >= the k-th largest (ties survive as far as the candidate list reaches)
+  const float thr = v[top_k - 1];
+  int kept = 0;
+  while (kept < nsel && v[kept] >= thr && v[kept] > -INFINITY) ++kept;
+  if (kept == 0) kept = 1;
+  float pr[kSelMax];
+  float sum = 0.f;
+  for (int r = 0; r < kept; ++r) { pr[r] = expf(v[r] - v[0]); sum += pr[r]; }
+  if (top_p > 0.f) {
+    // nucleus inside the kept set: drop entry r when the cumulative probability BEFORE it already exceeds top_p
+    float cum = 0.f; int keep2 = kept;
+    for (int r = 0; r < kept; ++r) {
+      if (r > 0 && cum > top_p) { keep2 = r; break; }
+      cum += pr[r] / sum;
+    }
+    kept = keep2;
+    sum = 0.f;
+    for (int r = 0; r < kept; ++r) sum += pr[r];
+  }
+  int choice = 0;
+  if (kept > 1 && top_k > 1) {     // top_k == 1 is the deterministic greedy path (lowest index among exact ties)
+    const uint64_t sd = d_seed ? *d_seed : seed;
+    const uint64_t h = splitmix64(sd ^ splitmix64(((uint64_t)row << 20) ^ (uint64_t)step));
+    const float u = (float)(h >> 40) * (1.0f / 16777216.0f) * sum;
+    float c = 0.f;
+    choice = kept - 1;
+    for (int r = 0; r < kept; ++r) { c += pr[r]; if (u < c) { choice = r; break; } }
+  }
+  const int tok = ix[choice];
+  if (step < T) seq[(int64_t)row * T + step] = tok;
+  cur_tokens[row] = tok;
+  if (step + 1 < prefix_stride) prefix[(int64_t)row * prefix_stride + step + 1] = (tok == eos) ? 0 : tok;
+  if (out_tokens) out_tokens[row] = tok;
+}
+
+__global__ void sample_finalize_kernel(int rows, int T, int eos, const int32_t* __restrict__ seq, int64_t* __restrict__ out_ids) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  bool ended = false;
+  for (int j = 0; j < T; ++j) {
+    const int tk = seq[(int64_t)row * T + j];
+    out_ids[(int64_t)row * T + j] = ended ? 0 : tk;
+    if (tk == eos) ended = true;
+  }
+}
+
+__global__ void step_advance_kernel(int* d_step) { if (threadIdx.x == 0 && blockIdx.x == 0) *d_step += 1; }
+
+__global__ void shift_labels_kernel(int L, int64_t* __restrict__ ids, int64_t* __restrict__ labels, int eos) {
+  const int b = blockIdx.x;
+  int64_t* row = ids + (int64_t)b * L;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) labels[(int64_t)b * L + i] = (i + 1 < L) ? row[i + 1] : 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < L; i += blockDim.x) if (row[i] == eos) row[i] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+ce_loss_kernel(int V, const float* __restrict__ logits, int64_t ldl, const int64_t* __restrict__ labels, float* __restrict__ loss) {
+  __shared__ float s_f[8];
+  __shared__ double s_d[8];
+  const int row = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t label = labels[row];
+  if (label == 0) { if (tid == 0) loss[row] = 0.f; return; }     // ignore_index = pad
+  const float* x = logits + (int64_t)row * ldl;
+  float m = -INFINITY;
+  for (int i = tid; i < V; i += 256) m = fmaxf(m, x[i]);
+  m = warp_max(m);
+  if (lane == 0) s_f[warp] = m;
+  __syncthreads();
+  m = s_f[lane & 7];
+  m = warp_max(m);
+  double acc = 0.0;
+  for (int i = tid; i < V; i += 256) acc += (double)expf(x[i] - m);
+  acc = warp_sum(acc);
+  if (lane == 0) s_d[warp] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += s_d[w];
+    loss[row] = (m + logf((float)tot)) - x[label];
+  }
+}
+
+__global__ void splice_kernel(int B, int Lt, int Lu, int64_t* ids, int64_t* seg, float* mask, int32_t* enc_len,
+                              const int64_t* __restrict__ utt, int segment_value, int strip_sep, int32_t* abnormal, int sep) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int64_t* row = ids + (int64_t)b * Lt;
+  const int64_t* u = utt + (int64_t)b * Lu;
+  int n = 0;
+  for (int j = 0; j < Lu; ++j) {
+    const int64_t tk = (strip_sep && u[j] == sep) ? 0 : u[j];
+    if (tk != 0) ++n;
+  }
+  const int start = enc_len[b];
+  int end = start + n;
+  if (end <= Lt) {
+    for (int j = 0; j < n; ++j) row[start + j] = (strip_sep && u[j] == sep) ? 0 : u[j];
+  } else {
+    if (start < Lt) row[start] = sep;
+    n = 1; end = start + 1;
+    if (abnormal) abnormal[b] = 1;
+  }
+  if (segment_value >= 0 && seg != nullptr)
+    for (int j = start; j < end && j < Lt; ++j) seg[(int64_t)b * Lt + j] = segment_value;
+  enc_len[b] = start + n;
+  if (mask != nullptr)
+    for (int j = 0; j < Lt; ++j) mask[(int64_t)b * Lt + j] = row[j] != 0 ? 1.f : 0.f;
+}
+
+__global__ void build_prefix_kernel(int rows, int len, const int64_t* __restrict__ prefix_ids, int32_t* prefix, int prefix_stride, int eos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * len) return;
+  const int r = i / len, j = i % len;
+  const int64_t tk = prefix_ids[i];
+  prefix[(int64_t)r * prefix_stride + j] = (tk == eos) ? 0 : (int32_t)tk;
+}
+
+}  // namespace
+
+int launch_row_select(int rows, int V, const float* logits, int64_t ldl, int mode, const float* row_bias, float temperature,
+                      const int32_t* ban_tokens, const int32_t* ban_count, int ban_stride, int nsel,
+                      float* sel_val, int32_t* sel_idx, float* logz, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (V > kSelThreads * kSlots) throw std::runtime_error("row_select: vocab > 32768");
+  if (nsel > kSelMax || nsel < 1) throw std::runtime_error("row_select: nsel out of range");
+  row_select_kernel<<<rows, kSelThreads, 0, stream>>>(V, logits, ldl, mode, row_bias, temperature, ban_tokens, ban_count,
+                                                      ban_stride, nsel, sel_val, sel_idx, logz);
+  return 1;
+}
+
+int launch_beam_init(const BeamBuffers& bb, int B, int K, int T, int start_token, cudaStream_t stream) {
+  const int n = B * K;
+  beam_init_kernel<<<(n + 255) / 256, 256, 0, stream>>>(bb, B, K, T, start_token);
+  return 1;
+}
+int launch_beam_step(const BeamBuffers& bb, int B, int K, int T, int V, int nsel, const float* sel_val,
+                     const int32_t* sel_idx, int eos, int32_t* out_beam_idx, int32_t* out_tokens, float* out_scores,
+                     cudaStream_t stream) {
+  if (K > 8 || T > kHypMaxT) throw std::runtime_error("beam_step: K <= 8 and T <= 32");
+  beam_step_kernel<<<(B + 31) / 32, 32, 0, stream>>>(bb, B, K, T, V, nsel, sel_val, sel_idx, eos, out_beam_idx, out_tokens, out_scores);
+  return 1;
+}
+int launch_beam_finalize(const BeamBuffers& bb, int B, int K, int T, int eos, int64_t* out_ids, float* out_scores,
+                         cudaStream_t stream) {
+  beam_finalize_kernel<<<(B + 31) / 32, 32, 0, stream>>>(bb, B, K, T, eos, out_ids, out_scores);
+  return 1;
+}
+int launch_ngram_ban(int rows, int Lh, const int64_t* hist_ids, const int64_t* hist_seg, const int32_t* prefix,
+                     int prefix_stride, const int* d_step, int n, int32_t* ban_tokens, int32_t* ban_count, int ban_stride,
+                     cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  ngram_ban_kernel<<<rows, 256, 0, stream>>>(Lh, hist_ids, hist_seg, prefix, prefix_stride, d_step, n, ban_tokens, ban_count, ban_stride);
+  return 1;
+}
+int launch_sample_step(int rows, int T, int nsel, const float* sel_val, const int32_t* sel_idx, int top_k, float top_p,
+                       uint64_t seed, const uint64_t* d_seed, const int* d_step, int eos, int32_t* seq, int32_t* cur_tokens, int32_t* prefix,
+                       int prefix_stride, int32_t* out_tokens, cudaStream_t stream) {
+  if (top_k < 1 || top_k > nsel) throw std::runtime_error("sample_step: top_k out of range");
+  sample_step_kernel<<<(rows + 63) / 64, 64, 0, stream>>>(rows, T, nsel, sel_val, sel_idx, top_k, top_p, seed, d_seed, d_step, eos, seq,
+                                                          cur_tokens, prefix, prefix_stride, out_tokens);
+  return 1;
+}
+int launch_sample_init(int rows, int T, int start_token, int32_t* seq, int32_t* cur_tokens, int32_t* prefix,
+                       int prefix_stride, int* d_step, cudaStream_t stream) {
+  sample_init_kernel<<<(rows + 63) / 64, 64, 0, stream>>>(rows, T, start_token, seq, cur_tokens, prefix, prefix_stride, d_step);
+  return 1;
+}
+int launch_sample_finalize(int rows, int T, int eos, const int32_t* seq, int64_t* out_ids, cudaStream_t stream) {
+  sample_finalize_kernel<<<(rows + 63) / 64, 64, 0, stream>>>(rows, T, eos, seq, out_ids);
+  return 1;
+}
+int launch_step_advance(int* d_step, cudaStream_t stream) {
+  step_advance_kernel<<<1, 32, 0, stream>>>(d_step);
+  return 1;
+}
+int launch_shift_labels(int B, int L, int64_t* dec_ids, int64_t* labels, int eos, cudaStream_t stream) {
+  shift_labels_kernel<<<B, 128, 0, stream>>>(L, dec_ids, labels, eos);
+  return 1;
+}
+int launch_ce_loss(int rows, int V, const float* logits, int64_t ldl, const int64_t* labels, float* loss, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  ce_loss_kernel<<<rows, 256, 0, stream>>>(V, logits, ldl, labels, loss);
+  return 1;
+}
+int launch_splice(int B, int Lt, int Lu, int64_t* ids, int64_t* seg, float* mask, int32_t* enc_len, const int64_t* utt,
+                  int segment_value, int strip_sep, int32_t* abnormal, int sep, cudaStream_t stream) {
+  splice_kernel<<<(B + 63) / 64, 64, 0, stream>>>(B, Lt, Lu, ids, seg, mask, enc_len, utt, segment_value, strip_sep, abnormal, sep);
+  return 1;
+}
+int launch_build_prefix_from_ids(int rows, int len, const int64_t* prefix_ids, int32_t* prefix, int prefix_stride, int eos,
+                                 cudaStream_t stream) {
+  const int n = rows * len;
+  if (n <= 0) return 0;
+  build_prefix_kernel<<<(n + 255) / 256, 256, 0, stream>>>(rows, len, prefix_ids, prefix, prefix_stride, eos);
+  return 1;
+}
+
+}  // namespace gstvd

@@ -1,0 +1,279 @@
+"""GPU: the whole hot path through the reference-shaped module API / C ABI against the oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star): fp32 logits <= 1e-3 max abs, greedy / beam ids identical in fp32;
+bf16: 2e-2 relative, defined here as rms(delta) / rms(reference) over the logits of valid positions.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import R, history_batch, load_golden, max_abs, rel_rms
+from oracle import beam as OB
+
+pytestmark = pytest.mark.gpu
+
+FP32_LOGIT_TOL = 1e-3
+BF16_REL_TOL = 2e-2
+
+
+def _params(enc_path, dec_path, dtype, model="enc_dec_a", mode="cc12m_gen", **kw):
+    p = {"model_enc_config": enc_path, "model_dec_config": dec_path, "gpu_ids": [0], "model": model, "mode": mode,
+         "compute_dtype": dtype, "engine_max_batch": 8, "engine_max_beams": 5}
+    p.update(kw)
+    return p
+
+
+def _build_model(enc_path, dec_path, sd, dtype, **kw):
+    from gst_visdial_b200.models.visual_dialog_decoder import VisualDialogDecoder
+    from gst_visdial_b200.models.visual_dialog_encoder import VisualDialogEncoder
+    from gst_visdial_b200.models.visual_dialog_model import EncoderDecoderModel
+    params = _params(enc_path, dec_path, dtype, **kw)
+    enc, dec = VisualDialogEncoder(params), VisualDialogDecoder(params)
+    dec.decoder.bert.embeddings = enc.bert_pretrained.bert.embeddings          # generate.py:65
+    model = EncoderDecoderModel(params, enc, dec)
+    model = torch.nn.DataParallel(model, [0])                                  # generate.py:67
+    model.module.load_state_dict(sd)                                           # generate.py:69
+    model.to("cuda:0").eval()
+    return model, params
+
+
+def _call(model, b, dec_ids=None, **kw):
+    dev = "cuda:0"
+    dec = b["dec_input_ids"].clone() if dec_ids is None else dec_ids
+    dec = dec.to(dev)
+    out = model(enc_image_features=b["enc_image_feat"].to(dev), enc_image_spatials=b["enc_image_loc"].to(dev),
+                enc_image_mask=b["enc_image_mask"].to(dev), enc_image_target=None, enc_image_label=None,
+                enc_next_sentence_labels=None, enc_input_ids=b["enc_input_ids"].to(dev), enc_segments=b["enc_segments"].to(dev),
+                enc_sep_indices=None, enc_mlm_labels=None, enc_attention_mask=b["enc_att_mask"].to(dev), dec_input_ids=dec,
+                dec_attention_mask=(dec != 0).float(), **kw)
+    return out, dec
+
+
+@pytest.fixture(scope="module")
+def tiny_fp32(tiny_sd):
+    from gst_visdial_b200 import weights as W
+    return _build_model(W.TINY_ENC_CONFIG, W.TINY_DEC_CONFIG, tiny_sd, "fp32")
+
+
+@pytest.fixture(scope="module")
+def tiny_bf16(tiny_sd):
+    from gst_visdial_b200 import weights as W
+    return _build_model(W.TINY_ENC_CONFIG, W.TINY_DEC_CONFIG, tiny_sd, "bf16")
+
+
+def test_tiny_fp32_encoder_matches_golden(tiny_fp32, tiny_cfgs, golden_dir):
+    model, _ = tiny_fp32
+    g = load_golden(golden_dir, "tiny_b3")
+    b = history_batch(tiny_cfgs[0], 0, 3)
+    eng = model.module._engine(torch.device("cuda:0"))
+    out = eng.encode(b["enc_input_ids"], b["enc_image_feat"], b["enc_image_loc"], b["enc_segments"], b["enc_att_mask"],
+                     b["enc_image_mask"], want_t=True, want_v=True, want_fused=True, want_nsp=True)
+    assert max_abs(out["seq_v"].cpu(), torch.from_numpy(g["seq_v"])) < 1e-3
+    assert max_abs(out["seq_t"].cpu(), torch.from_numpy(g["seq_t"])) < 1e-3
+    assert max_abs(out["fused"].cpu(), torch.from_numpy(g["fused"])) < 1e-3
+    assert max_abs(out["nsp"].cpu(), torch.from_numpy(g["nsp"])) < 1e-3
+    assert torch.equal(out["fused_mask"].cpu(), torch.cat((b["enc_image_mask"], b["enc_att_mask"]), 1))
+    # the wrapper returns the reference's 7-tuple
+    tup = model.module.encoder(b["enc_input_ids"].cuda(), b["enc_image_feat"].cuda(), b["enc_image_loc"].cuda(),
+                               token_type_ids=b["enc_segments"].cuda(), attention_mask=b["enc_att_mask"].cuda(),
+                               image_attention_mask=b["enc_image_mask"].cuda())
+    assert len(tup) == 7 and tup[0] is None and max_abs(tup[5].cpu(), torch.from_numpy(g["seq_t"])) < 1e-3
+
+
+def test_tiny_fp32_greedy_ngram_score_match_golden(tiny_fp32, tiny_cfgs, golden_dir):
+    model, params = tiny_fp32
+    g = load_golden(golden_dir, "tiny_b3")
+    b = history_batch(tiny_cfgs[0], 0, 3)
+    seq, _ = _call(model, b, temperature=1.0, top_k=1, top_p=0.0, ngram_blocking_size=0)
+    assert np.array_equal(seq.cpu().numpy(), g["greedy_ids"]), f"{seq.cpu().numpy()} vs {g['greedy_ids']}"
+    seq_ng, _ = _call(model, b, temperature=0.7, top_k=1, top_p=0.0, ngram_blocking_size=4)
+    assert np.array_equal(seq_ng.cpu().numpy(), g["greedy_ng4_ids"])
+    # teacher-forced logits along the greedy path, then the perplexity pass of generate.py:183-209
+    params["mode"] = "train"
+    try:
+        dec_in = torch.cat((b["dec_input_ids"], torch.from_numpy(g["greedy_ids"])[:, :-1]), 1)
+        (loss, logits), _ = _call(model, b, dec_ids=dec_in, loss_reduction=False)
+        assert max_abs(logits.cpu(), torch.from_numpy(g["greedy_logits"])) < FP32_LOGIT_TOL
+        ans = torch.from_numpy(g["greedy_ids"]).clone()
+        (loss, logits), ans_dev = _call(model, b, dec_ids=ans, loss_reduction=False)
+        assert loss.shape == (3 * 18,)
+        assert max_abs(loss.cpu().reshape(3, 18), torch.from_numpy(g["score_loss"])) < FP32_LOGIT_TOL
+        assert max_abs(logits.cpu(), torch.from_numpy(g["score_logits"])) < FP32_LOGIT_TOL
+        assert not (ans_dev == 102).any(), "dec_input_ids must be modified in place like the reference does"
+        ans_len = (ans_dev != 0).sum(-1)
+        ppl = torch.exp(loss.reshape(3, 18).sum(-1) / ans_len)
+        assert np.allclose(ppl.cpu().numpy(), g["score_ppl"], rtol=2e-3)
+        # mean reduction + reuse of the resident encoder state
+        (loss_m, _), _ = _call(model, b, dec_ids=torch.from_numpy(g["greedy_ids"]).clone(), loss_reduction=True, reuse_encoder=True)
+        sl = torch.from_numpy(g["score_loss"])
+        assert abs(loss_m.item() - (sl.sum() / (sl != 0).sum()).item()) < 1e-3
+    finally:
+        params["mode"] = "cc12m_gen"
+
+
+def test_tiny_fp32_beam_matches_oracle(tiny_fp32, tiny_cfgs, tiny_sd):
+    model, _ = tiny_fp32
+    enc_cfg, dec_cfg = tiny_cfgs
+    b = history_batch(enc_cfg, 0, 3)
+    with torch.no_grad():
+        ref_seq, ref_sc = OB.beam_search(tiny_sd, enc_cfg, dec_cfg, b, num_beams=5)
+    seq, _ = _call(model, b, temperature=1.0, top_k=1, top_p=0.0, ngram_blocking_size=0, num_beams=5)
+    assert torch.equal(seq.cpu(), ref_seq), f"{seq.cpu()} vs {ref_seq}"
+    eng = model.module._engine(torch.device("cuda:0"))
+    seq2, sc2 = eng.generate(3, num_beams=5, want_scores=True)
+    assert torch.equal(seq2.cpu(), ref_seq) and torch.allclose(sc2.cpu().double(), ref_sc, atol=1e-4)
+
+
+def test_tiny_eos_handling(tiny_cfgs, tiny_sd):
+    """Make [SEP] likely (large lm_head bias) so that EOS->PAD in the prefix, PAD-after-EOS and beam hypotheses are exercised."""
+    from gst_visdial_b200 import weights as W
+    enc_cfg, dec_cfg = tiny_cfgs
+    sd = dict(tiny_sd)
+    bias = sd["decoder.decoder.lm_head.bias"].clone()
+    bias[102] += 2.5
+    sd["decoder.decoder.lm_head.bias"] = bias
+    sd["decoder.decoder.lm_head.decoder.bias"] = bias
+    model, _ = _build_model(W.TINY_ENC_CONFIG, W.TINY_DEC_CONFIG, sd, "fp32")
+    b = history_batch(enc_cfg, 0, 3)
+    with torch.no_grad():
+        ref = R.generate_greedy_or_sample(sd, enc_cfg, dec_cfg, b, 1.0, 1, 0.0, 0)
+        ref_beam, _ = OB.beam_search(sd, enc_cfg, dec_cfg, b, num_beams=3)
+    assert (ref == 102).any(), "test needs an EOS in the greedy output; raise the bias"
+    seq, _ = _call(model, b, temperature=1.0, top_k=1, top_p=0.0, ngram_blocking_size=0)
+    assert torch.equal(seq.cpu(), ref)
+    seqb, _ = _call(model, b, temperature=1.0, top_k=1, top_p=0.0, ngram_blocking_size=0, num_beams=3)
+    assert torch.equal(seqb.cpu(), ref_beam)
+
+
+def test_tiny_graph_equals_eager(tiny_cfgs, tiny_sd):
+    from gst_visdial_b200 import _lib
+    from gst_visdial_b200.engine import Engine
+    enc_cfg, dec_cfg = tiny_cfgs
+    b = history_batch(enc_cfg, 0, 3)
+    outs = []
+    for flags in (0, _lib.GSTVD_FLAG_NO_CUDA_GRAPH):
+        e = Engine(enc_cfg, dec_cfg, dtype="fp32", max_batch=4, flags=flags)
+        e.load_state_dict(tiny_sd)
+        enc = e.encode(b["enc_input_ids"], b["enc_image_feat"], b["enc_image_loc"], b["enc_segments"], b["enc_att_mask"], b["enc_image_mask"])
+        e.prefill_cross(3, enc["Le"])
+        o1 = e.generate(3, num_beams=5).cpu()
+        o2 = e.generate(3, num_beams=1, top_k=1).cpu()
+        o3 = e.generate(3, num_beams=5).cpu()          # replay of the cached graph
+        assert torch.equal(o1, o3)
+        assert e.launch_count > 0
+        outs.append((o1, o2))
+        e.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_tiny_bf16_within_tolerance(tiny_bf16, tiny_cfgs, golden_dir):
+    model, params = tiny_bf16
+    g = load_golden(golden_dir, "tiny_b3")
+    b = history_batch(tiny_cfgs[0], 0, 3)
+    eng = model.module._engine(torch.device("cuda:0"))
+    out = eng.encode(b["enc_input_ids"], b["enc_image_feat"], b["enc_image_loc"], b["enc_segments"], b["enc_att_mask"],
+                     b["enc_image_mask"], want_t=True, want_v=True, want_fused=True, want_nsp=True)
+    valid = b["enc_att_mask"].bool()
+    rt = rel_rms(out["seq_t"].cpu()[valid], torch.from_numpy(g["seq_t"])[valid])
+    rv = rel_rms(out["seq_v"].cpu(), torch.from_numpy(g["seq_v"]))
+    print(f"bf16 encoder rel rms: text {rt:.4f} image {rv:.4f}")
+    assert rt < BF16_REL_TOL and rv < BF16_REL_TOL
+    params["mode"] = "train"
+    try:
+        dec_in = torch.cat((b["dec_input_ids"], torch.from_numpy(g["greedy_ids"])[:, :-1]), 1)
+        (loss, logits), _ = _call(model, b, dec_ids=dec_in, loss_reduction=False)
+    finally:
+        params["mode"] = "cc12m_gen"
+    rl = rel_rms(logits.cpu(), torch.from_numpy(g["greedy_logits"]))
+    print(f"bf16 greedy-path logits rel rms {rl:.4f}, max abs {max_abs(logits.cpu(), torch.from_numpy(g['greedy_logits'])):.4f}")
+    assert rl < BF16_REL_TOL
+    seq, _ = _call(model, b, temperature=1.0, top_k=1, top_p=0.0, ngram_blocking_size=0)
+    agree = (seq.cpu().numpy() == g["greedy_ids"]).mean()
+    print(f"bf16 greedy token agreement with fp32 reference: {agree:.3f}")
+    assert seq.shape == (3, 18)
+
+
+def test_tiny_sampling_runs_and_is_seeded(tiny_bf16, tiny_cfgs):
+    model, _ = tiny_bf16
+    b = history_batch(tiny_cfgs[0], 0, 3)
+    a, _ = _call(model, b, temperature=0.7, top_k=7, top_p=0.0, ngram_blocking_size=4, seed=11)
+    c, _ = _call(model, b, temperature=0.7, top_k=7, top_p=0.0, ngram_blocking_size=4, seed=11)
+    d, _ = _call(model, b, temperature=0.7, top_k=7, top_p=0.0, ngram_blocking_size=4, seed=12)
+    assert torch.equal(a, c) and a.shape == (3, 18) and a.dtype == torch.int64
+    assert not torch.equal(a, d)
+
+
+def test_enc_only_nsp(tiny_cfgs, tiny_sd, golden_dir):
+    from gst_visdial_b200 import weights as W
+    from gst_visdial_b200.models.visual_dialog_encoder import VisualDialogEncoder
+    g = load_golden(golden_dir, "tiny_b3")
+    params = _params(W.TINY_ENC_CONFIG, W.TINY_DEC_CONFIG, "fp32", model="enc_only_a", mode="vd_eval_val")
+    enc = VisualDialogEncoder(params)
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in tiny_sd.items() if k.startswith("encoder.")})
+    enc.to("cuda:0").eval()
+    b = history_batch(tiny_cfgs[0], 0, 3)
+    out = enc(b["enc_input_ids"].cuda(), b["enc_image_feat"].cuda(), b["enc_image_loc"].cuda(), token_type_ids=b["enc_segments"].cuda(),
+              attention_mask=b["enc_att_mask"].cuda(), image_attention_mask=b["enc_image_mask"].cuda())
+    assert out[5] is None and max_abs(out[3].cpu(), torch.from_numpy(g["nsp"])) < 1e-3
+
+
+# ---- full-size model (config/bert_base_6layer_6conect_*.json) ---------------------------------------------------------
+@pytest.fixture(scope="module")
+def full_engines(full_cfgs, full_sd):
+    from gst_visdial_b200.engine import Engine
+    enc_cfg, dec_cfg = full_cfgs
+    e32 = Engine(enc_cfg, dec_cfg, dtype="fp32", max_batch=4)
+    e32.load_state_dict(full_sd)
+    e16 = Engine(enc_cfg, dec_cfg, dtype="bf16", max_batch=4)
+    e16.load_state_dict(full_sd)
+    yield e32, e16
+    e32.close(); e16.close()
+
+
+def test_full_fp32_config1_matches_reference_golden(full_engines, full_cfgs, golden_dir):
+    """BASELINE.json configs[0]: teacher enc_dec_a, greedy, batch 1, fp32 - token ids identical, logits <= 1e-3."""
+    e32, _ = full_engines
+    g = load_golden(golden_dir, "full_b1")
+    b = history_batch(full_cfgs[0], 0, 1)
+    out = e32.encode(b["enc_input_ids"], b["enc_image_feat"], b["enc_image_loc"], b["enc_segments"], b["enc_att_mask"], b["enc_image_mask"],
+                     want_t=True, want_v=True, want_fused=True, want_nsp=True)
+    assert max_abs(out["seq_t"].cpu()[:, :48, :32], torch.from_numpy(g["seq_t_slice"])) < 1e-3
+    assert max_abs(out["seq_v"].cpu()[:, :, :32], torch.from_numpy(g["seq_v_slice"])) < 1e-3
+    assert max_abs(out["fused"].cpu()[:, :, :24], torch.from_numpy(g["fused_slice"])) < 1e-3
+    assert max_abs(out["fused"].cpu().sum(-1), torch.from_numpy(g["fused_rowsum"])) < 2e-2
+    assert max_abs(out["nsp"].cpu(), torch.from_numpy(g["nsp"])) < 1e-3
+    e32.prefill_cross(1, out["Le"])
+    seq = e32.generate(1, num_beams=1, top_k=1, temperature=1.0)
+    assert np.array_equal(seq.cpu().numpy(), g["greedy_ids"]), f"{seq.cpu().numpy()} vs {g['greedy_ids']}"
+    dec_in = torch.cat((b["dec_input_ids"], torch.from_numpy(g["greedy_ids"])[:, :-1]), 1).cuda()
+    _, logits = e32.score(dec_in, None, labels=torch.zeros_like(dec_in), want_logits=True)
+    lg = logits.cpu()
+    assert max_abs(lg[:, :, :256], torch.from_numpy(g["greedy_logits_slice"])) < FP32_LOGIT_TOL
+    assert max_abs(torch.logsumexp(lg, -1), torch.from_numpy(g["greedy_logits_lse"])) < FP32_LOGIT_TOL
+    top = lg.topk(8, dim=-1)
+    assert np.array_equal(top.indices.numpy(), g["greedy_logits_top_idx"])
+    ans = torch.from_numpy(g["greedy_ids"]).clone().cuda()
+    loss, _ = e32.score(ans, (ans != 0).float())
+    assert max_abs(loss.cpu(), torch.from_numpy(g["score_loss"])) < FP32_LOGIT_TOL
+
+
+def test_full_bf16_vs_fp32(full_engines, full_cfgs, golden_dir):
+    e32, e16 = full_engines
+    g = load_golden(golden_dir, "full_b1")
+    b = history_batch(full_cfgs[0], 0, 3)
+    outs = []
+    for e in (e32, e16):
+        o = e.encode(b["enc_input_ids"], b["enc_image_feat"], b["enc_image_loc"], b["enc_segments"], b["enc_att_mask"], b["enc_image_mask"],
+                     want_t=True, want_v=True)
+        e.prefill_cross(3, o["Le"])
+        dec_in = torch.cat((b["dec_input_ids"].repeat(1, 1), torch.from_numpy(g["greedy_ids"]).repeat(3, 1)[:, :-1]), 1).cuda()
+        _, lg = e.score(dec_in, None, labels=torch.zeros_like(dec_in), want_logits=True)
+        outs.append((o["seq_t"].cpu(), o["seq_v"].cpu(), lg.cpu()))
+    valid = b["enc_att_mask"].bool()
+    rt = rel_rms(outs[1][0][valid], outs[0][0][valid]); rv = rel_rms(outs[1][1], outs[0][1]); rl = rel_rms(outs[1][2], outs[0][2])
+    print(f"full model bf16 vs fp32: text {rt:.4f} image {rv:.4f} logits {rl:.4f} (max abs {max_abs(outs[1][2], outs[0][2]):.4f})")
+    assert rt < BF16_REL_TOL and rv < BF16_REL_TOL and rl < BF16_REL_TOL
+    s16 = e16.generate(3, num_beams=5)
+    s32 = e32.generate(3, num_beams=5)
+    print("beam-5 token agreement bf16 vs fp32:", (s16 == s32).float().mean().item())
+    assert s16.shape == (3, 18)
