@@ -1,0 +1,85 @@
+"""Ten-round synthetic dialog generation: the loop of the reference's generate.py:122-233 without its host syncs.
+
+Per round: question (questioner model, or a caller-supplied utterance) -> splice into the history ->
+answer (teacher model) -> optional perplexity pass over the answer (generate.py:183-209) -> splice the answer with
+segment 1.  History state stays on the device; the splices run in the engine's integer kernels (gstvd_splice), so
+nothing in a round waits for the host.
+
+Reference quirks kept: the answer reaches the history WITHOUT its [SEP] (the perplexity pass
+replaces [SEP] by [PAD] in place before the splice, single-device behaviour); overflow past max_seq_len writes a
+lone [SEP] and marks the dialog abnormal; ppl = exp(sum CE / count(ids != 0)) with the first answer token unscored.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+
+@dataclass
+class DialogResult:
+    questions: torch.Tensor      # int64 [B, rounds, 18]
+    answers: torch.Tensor        # int64 [B, rounds, 18]  ([SEP] already replaced by [PAD] when ppl was computed)
+    answer_ppl: Optional[torch.Tensor]   # fp32 [B, rounds] or None
+    abnormal: torch.Tensor       # int32 [B] (1 = history overflowed, dropped from the output like generate.py:236-237)
+    enc_input_ids: torch.Tensor  # final history [B, max_seq_len]
+
+
+def _unwrap(model):
+    return model.module if hasattr(model, "module") else model
+
+
+def _model_call(model, st, dec_input_ids, **kw):
+    return model(
+        enc_image_features=st["feat"], enc_image_spatials=st["loc"], enc_image_mask=st["imask"], enc_image_target=None,
+        enc_image_label=None, enc_next_sentence_labels=None, enc_input_ids=st["ids"], enc_segments=st["seg"], enc_sep_indices=None,
+        enc_mlm_labels=None, enc_attention_mask=st["mask"], dec_input_ids=dec_input_ids,
+        dec_attention_mask=(dec_input_ids != 0).float(), **kw)
+
+
+def generate_dialogs(a_model, batch, q_model=None, questions=None, num_rounds=10, a_kwargs=None, q_kwargs=None,
+                     with_ppl=True, device=None) -> DialogResult:
+    """``batch`` uses the reference dataloader's keys (generate.py:95-111).  Either ``q_model`` or ``questions``
+    (int64 [B, num_rounds, 18], zero padded, each ending in [SEP]) must be given.  ``a_kwargs`` / ``q_kwargs`` are the
+    decoding kwargs of EncoderDecoderModel.forward; defaults are generate.py:138-141 / :177-180."""
+    a_kwargs = dict(a_kwargs or dict(temperature=0.7, top_k=7, top_p=0.0, ngram_blocking_size=0))
+    q_kwargs = dict(q_kwargs or dict(temperature=0.7, top_k=7, top_p=0.0, ngram_blocking_size=4))
+    am = _unwrap(a_model)
+    dev = torch.device(device) if device is not None else next(am.parameters()).device
+    eng = am._engine(dev)
+    nb = dict(device=dev, non_blocking=True)
+    st = {
+        "feat": batch["enc_image_feat"].to(dtype=torch.float32, **nb), "loc": batch["enc_image_loc"].to(dtype=torch.float32, **nb),
+        "imask": batch["enc_image_mask"].to(dtype=torch.float32, **nb),
+        "ids": batch["enc_input_ids"].to(dtype=torch.int64, **nb).clone().contiguous(),
+        "seg": batch["enc_segments"].to(dtype=torch.int64, **nb).clone().contiguous(),
+    }
+    B = st["ids"].shape[0]
+    st["mask"] = (st["ids"] != 0).float()
+    enc_len = (st["ids"] != 0).sum(-1).to(torch.int32)
+    abnormal = torch.zeros(B, dtype=torch.int32, device=dev)
+    dec_start = batch["dec_input_ids"].to(dtype=torch.int64, **nb)
+    if questions is not None:
+        questions = questions.to(dtype=torch.int64, **nb)
+    elif q_model is None:
+        raise ValueError("generate_dialogs needs q_model or questions")
+    ques_all, ans_all, ppl_all = [], [], []
+    mode = am.params["mode"]
+    for rnd in range(num_rounds):
+        ques = questions[:, rnd].contiguous() if q_model is None else _model_call(q_model, st, dec_start, **q_kwargs)
+        eng.splice(st["ids"], st["seg"], st["mask"], enc_len, ques, segment_value=-1, strip_sep=False, abnormal=abnormal)
+        ans = _model_call(a_model, st, dec_start, **a_kwargs)
+        if with_ppl:
+            am.params["mode"] = "train"                      # the reference's mode-flip trick (generate.py:185,211)
+            try:
+                loss, _ = _model_call(a_model, st, ans, loss_reduction=False, reuse_encoder=True, want_logits=False)
+            finally:
+                am.params["mode"] = mode
+            ans_len = (ans != 0).sum(-1)                     # counted after the in-place [SEP] -> [PAD]
+            ppl_all.append(torch.exp(loss.reshape(B, -1).sum(-1) / ans_len))
+        eng.splice(st["ids"], st["seg"], st["mask"], enc_len, ans, segment_value=1, strip_sep=True, abnormal=abnormal)
+        ques_all.append(ques)
+        ans_all.append(ans)
+    return DialogResult(torch.stack(ques_all, 1), torch.stack(ans_all, 1), torch.stack(ppl_all, 1) if with_ppl else None,
+                        abnormal, st["ids"])

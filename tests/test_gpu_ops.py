@@ -132,7 +132,9 @@ def test_attention_fully_masked_row_is_uniform(eng):
     mask = torch.zeros(1, 4)
     y = eng.op_attention(q, k, v, 2, mask, neg=-10000.0, causal=False, dtype="fp32").cpu()
     ref = _ref_attention(q, k, v, 2, mask, -10000.0, False)
-    assert torch.isfinite(y).all() and max_abs(y, ref) < 1e-4
+    # adding -10000 in fp32 quantises the scores to ~1e-3 (the reference's fp32 arithmetic does the same), hence the tolerance
+    assert torch.isfinite(y).all() and max_abs(y, ref) < 5e-3
+    assert max_abs(y, v.mean(1, keepdim=True).expand_as(y)) < 0.2
 
 
 @pytest.mark.parametrize("B,K", [(3, 5), (2, 1), (4, 2)])
@@ -187,9 +189,9 @@ def test_sample_greedy_topk_and_ngram(eng, full_cfgs):
         assert tok2[r].item() == step.argmax(-1).item()
     assert tok2[0].item() != 5003 and tok2[3].item() == 5003 and tok2[4].item() == 5003
     # top-k sampling stays inside the top-k set and follows the softmax of the kept logits
-    lg = torch.zeros(8, V)
+    lg = torch.full((8, V), -5.0)
     lg[:, 100:107] = torch.tensor([3.0, 2.5, 2.0, 1.5, 1.0, 0.5, 0.0])
-    lg[:, 200] = -0.5
+    lg[:, 200] = -0.5          # 8th largest: must never be drawn with top_k = 7
     counts = torch.zeros(7)
     n = 0
     for s in range(200):

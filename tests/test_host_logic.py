@@ -1,0 +1,96 @@
+"""CPU: host-side logic - key layout of the boundary modules, synthetic generators, sharding + gather (gloo, world 2)."""
+import os
+import subprocess
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_module_state_dict_layout_matches_spec(tiny_cfgs, tiny_sd):
+    from gst_visdial_b200 import weights as W
+    from gst_visdial_b200.models.visual_dialog_decoder import VisualDialogDecoder
+    from gst_visdial_b200.models.visual_dialog_encoder import VisualDialogEncoder
+    from gst_visdial_b200.models.visual_dialog_model import EncoderDecoderModel
+    params = {"model_enc_config": W.TINY_ENC_CONFIG, "model_dec_config": W.TINY_DEC_CONFIG, "gpu_ids": [0], "model": "enc_dec_a",
+              "mode": "cc12m_gen"}
+    enc, dec = VisualDialogEncoder(params), VisualDialogDecoder(params)
+    dec.decoder.bert.embeddings = enc.bert_pretrained.bert.embeddings
+    model = EncoderDecoderModel(params, enc, dec)
+    spec = W.model_spec(*tiny_cfgs)
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(spec.keys()) or set(sd.keys()) == set(spec.keys())
+    assert all(tuple(sd[k].shape) == tuple(spec[k]) for k in spec)
+    v0 = model._version.value
+    model.load_state_dict(tiny_sd, strict=True)
+    assert model._version.value > v0
+    w = model.encoder.bert_pretrained.bert.embeddings.word_embeddings.weight
+    assert model.decoder.decoder.bert.embeddings.word_embeddings.weight is w          # generate.py:65 aliasing survives
+    assert torch.equal(w, tiny_sd["encoder.bert_pretrained.bert.embeddings.word_embeddings.weight"])
+    assert hasattr(model.decoder.config, "eos_token_id") and model.decoder.config.eos_token_id == 102
+    assert model.decoder.decoder.config.vocab_size == tiny_cfgs[1].vocab_size
+    assert "hidden_size" in model.encoder.config.to_dict()
+    # the full 6-layer/6-connect layout has the 861 keys of the released checkpoints
+    full = W.model_spec(W.load_json_config(W.DEFAULT_ENC_CONFIG), W.load_json_config(W.DEFAULT_DEC_CONFIG))
+    assert len(full) == 861
+
+
+def test_modules_refuse_cpu_tensors(tiny_cfgs):
+    import pytest
+    from gst_visdial_b200 import synthetic as S
+    from gst_visdial_b200 import weights as W
+    from gst_visdial_b200.models.visual_dialog_encoder import VisualDialogEncoder
+    params = {"model_enc_config": W.TINY_ENC_CONFIG, "model_dec_config": W.TINY_DEC_CONFIG, "gpu_ids": [0], "model": "enc_only_a",
+              "mode": "vd_eval_val"}
+    enc = VisualDialogEncoder(params)
+    b = S.synthetic_batch(0, 1, vocab_size=tiny_cfgs[0].vocab_size, v_feature_size=tiny_cfgs[0].v_feature_size)
+    with pytest.raises(RuntimeError):
+        enc(b["enc_input_ids"], b["enc_image_feat"], b["enc_image_loc"])
+
+
+def test_synthetic_inputs_are_shard_invariant():
+    from gst_visdial_b200 import synthetic as S
+    a = S.synthetic_batch(0, 6, vocab_size=1000, v_feature_size=64)
+    b = S.synthetic_batch(4, 2, vocab_size=1000, v_feature_size=64)
+    assert torch.equal(a["enc_input_ids"][4:], b["enc_input_ids"]) and torch.equal(a["enc_image_feat"][4:], b["enc_image_feat"])
+    assert (a["enc_image_feat"][:, 0] - a["enc_image_feat"][:, 1:].mean(1)).abs().max() < 1e-5      # global row = mean
+    assert a["enc_input_ids"][:, 0].eq(101).all() and (a["enc_att_mask"] == (a["enc_input_ids"] != 0).float()).all()
+
+
+def test_shard_range_partitions():
+    from gst_visdial_b200.dist import shard_range
+    for total in (0, 1, 7, 64, 257):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                s, e = shard_range(total, r, world)
+                seen.extend(range(s, e))
+            assert seen == list(range(total))
+
+
+WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, sys.argv[1])
+from gst_visdial_b200 import dist as D
+rank, world, _ = D.init_from_env("gloo")
+total = 7
+s, e = D.shard_range(total, rank, world)
+ids = torch.arange(s, e).view(-1, 1).repeat(1, 3) * 10 + rank
+ppl = torch.arange(s, e).float() + 0.5
+counts = [D.shard_range(total, r, world)[1] - D.shard_range(total, r, world)[0] for r in range(world)]
+g_ids, g_ppl = D.gather_results([ids, ppl], counts)
+assert g_ids.shape == (total, 3) and g_ppl.tolist() == [i + 0.5 for i in range(total)], (g_ids, g_ppl)
+assert (g_ids[:, 0] // 10).tolist() == list(range(total))
+print("rank", rank, "ok")
+"""
+
+
+def test_gather_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
