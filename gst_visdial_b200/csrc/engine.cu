@@ -105,6 +105,10 @@ struct gstvd_ctx {
   int op_B = 0, op_K = 0, op_T = 0;
 
   std::map<GraphKey, cudaGraphExec_t> graphs;
+  // optional event profiling of the tcgen05 GEMM launches (bench.py roofline): one event pair per launch
+  bool profiling = false; int prof_min_rows = 0;
+  struct ProfRec { cudaEvent_t a, b; double flops, bytes; };
+  std::vector<ProfRec> prof_pool; size_t prof_used = 0;
   cudaStream_t own_stream = nullptr;     // decode steps run (and are graph-captured) here: the caller may be on the legacy stream
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 
@@ -322,7 +326,19 @@ struct Exec {
     else {
       a.W = L.w16;
       if (c->cfg.flags & GSTVD_FLAG_DEBUG_SIMT_GEMM) c->launches += launch_gemm_simt(a, kBF16, s);
-      else c->launches += launch_gemm_tc(a, c->num_sms, s);
+      else {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        const bool prof = c->profiling && M >= c->prof_min_rows && c->prof_used < c->prof_pool.size() &&
+                          cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone;
+        if (prof) cudaEventRecord(c->prof_pool[c->prof_used].a, s);
+        c->launches += launch_gemm_tc(a, c->num_sms, s);
+        if (prof) {
+          auto& r = c->prof_pool[c->prof_used++];
+          cudaEventRecord(r.b, s);
+          r.flops = 2.0 * M * (double)L.out * L.in;
+          r.bytes = 2.0 * ((double)M * L.in + (double)L.out * L.in) + (out_f32 ? 4.0 : 2.0) * M * (double)L.out;
+        }
+      }
     }
   }
   void add_ln(const void* x, const void* res, const LNp& l, void* y, int rows) {
@@ -751,6 +767,7 @@ void gstvd_destroy(gstvd_ctx* c) {
                     &c->logz, &c->ban_tokens, &c->ban_count, &c->prefix, &c->seq, &c->beam_scores, &c->beam_tokens, &c->cur_tokens,
                     &c->beam_idx, &c->beam_done, &c->hyp_score, &c->hyp_len, &c->hyp_tokens, &c->hyp_count, &c->hyp_worst, &c->d_step, &c->d_seed};
   for (DevBuf* b : bufs) b->release();
+  for (auto& r : c->prof_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (c->ev_in) cudaEventDestroy(c->ev_in);
   if (c->ev_out) cudaEventDestroy(c->ev_out);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -849,6 +866,32 @@ int gstvd_splice(gstvd_ctx* c, int B, int Lt, int Lu, int64_t* enc_input_ids, in
 }
 
 int64_t gstvd_launch_count(const gstvd_ctx* c) { return c ? c->launches : -1; }
+
+int gstvd_profile_gemm(gstvd_ctx* c, int enable, int min_rows) {
+  if (!c) return GSTVD_ERR_INVALID;
+  return guarded(c, [&] {
+    if (enable && c->prof_pool.empty()) {
+      c->prof_pool.resize(8192);
+      for (auto& r : c->prof_pool) { CUDA_CHECK(cudaEventCreate(&r.a)); CUDA_CHECK(cudaEventCreate(&r.b)); }
+    }
+    c->profiling = enable != 0; c->prof_min_rows = min_rows; c->prof_used = 0;
+  });
+}
+
+int gstvd_profile_read(gstvd_ctx* c, double* flops, double* bytes, double* ms, int64_t* launches) {
+  if (!c) return GSTVD_ERR_INVALID;
+  return guarded(c, [&] {
+    CUDA_CHECK(cudaDeviceSynchronize());
+    double f = 0, by = 0, t = 0;
+    for (size_t i = 0; i < c->prof_used; ++i) {
+      float e = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&e, c->prof_pool[i].a, c->prof_pool[i].b));
+      f += c->prof_pool[i].flops; by += c->prof_pool[i].bytes; t += e;
+    }
+    if (flops) *flops = f; if (bytes) *bytes = by; if (ms) *ms = t; if (launches) *launches = (int64_t)c->prof_used;
+    c->prof_used = 0;
+  });
+}
 
 // ---- single operators ------------------------------------------------------------------------------------------
 int gstvd_op_linear(gstvd_ctx* c, int dtype, int M, int N, int K, const float* a, const float* w, const float* bias, int act, float* out,

@@ -89,6 +89,14 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.gstvd_launch_count(self.ctx))
 
+    def profile_gemm(self, enable: bool, min_rows: int = 0):
+        check(self.ctx, self.lib.gstvd_profile_gemm(self.ctx, int(enable), int(min_rows)))
+
+    def profile_read(self):
+        f, b, ms, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        check(self.ctx, self.lib.gstvd_profile_read(self.ctx, ctypes.byref(f), ctypes.byref(b), ctypes.byref(ms), ctypes.byref(n)))
+        return dict(flops=f.value, bytes=b.value, ms=ms.value, launches=n.value)
+
     # ---- weights --------------------------------------------------------------------------------------------
     def load_state_dict(self, sd: Mapping[str, torch.Tensor], prefix: str = "", strict: bool = True):
         """``sd`` uses EncoderDecoderModel key names after ``prefix`` is prepended (e.g. prefix='encoder.' for a bare

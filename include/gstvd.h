@@ -194,6 +194,13 @@ int gstvd_op_sample(gstvd_ctx* ctx, int rows, const float* logits, int64_t ldl, 
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t gstvd_launch_count(const gstvd_ctx* ctx);
 
+/* Measurement aid for bench.py's roofline: while enabled, every tcgen05 GEMM launch with at least `min_rows` rows that is
+ * issued eagerly (not inside a captured decode graph) is bracketed by a CUDA event pair on its own stream.
+ * gstvd_profile_read synchronises the device, returns the summed algorithmic FLOPs (2*M*N*K), algorithmic bytes
+ * (operands read once + output written once), summed event time in ms and the number of launches, and resets. */
+int gstvd_profile_gemm(gstvd_ctx* ctx, int enable, int min_rows);
+int gstvd_profile_read(gstvd_ctx* ctx, double* flops, double* bytes, double* ms, int64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

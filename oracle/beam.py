@@ -134,13 +134,16 @@ def reorder_cache(past, beam_idx):
     return tuple(tuple(p.index_select(0, beam_idx) for p in layer) for layer in past)
 
 
-def beam_search(sd, enc_cfg, dec_cfg, batch, num_beams=5, max_new=18, return_trace=False):
+def beam_search(sd, enc_cfg, dec_cfg, batch, num_beams=5, max_new=18, return_trace=False, precomputed_encoder=None):
     """Full beam search over the restated reference modules (no KV cache, whole prefix every step, encoder
     states repeated per beam - the way the reference's ``use_cache=False`` decoder would have to be driven)."""
     from . import restatement as R
     ids, seg, att = batch["enc_input_ids"], batch["enc_segments"], batch["enc_att_mask"]
     B, K = ids.shape[0], num_beams
-    seq_t, seq_v = R.encoder(sd, enc_cfg, ids, batch["enc_image_feat"], batch["enc_image_loc"], seg, att, batch["enc_image_mask"])
+    if precomputed_encoder is not None:
+        seq_t, seq_v = precomputed_encoder
+    else:
+        seq_t, seq_v = R.encoder(sd, enc_cfg, ids, batch["enc_image_feat"], batch["enc_image_loc"], seg, att, batch["enc_image_mask"])
     enc_h, enc_m = R.vlfusion(sd, seq_t, seq_v, att, batch["enc_image_mask"])
     enc_h = enc_h.repeat_interleave(K, 0); enc_m = enc_m.repeat_interleave(K, 0)
     st = BeamState(B, K, dec_cfg.vocab_size, max_new)

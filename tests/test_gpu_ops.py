@@ -125,8 +125,8 @@ def test_attention(eng, dtype, tol, B, heads, Lq, Lk, D, causal, neg):
     assert max_abs(y, ref) < tol, f"max abs {max_abs(y, ref)}"
 
 
-def test_attention_fully_masked_row_is_uniform(eng):
-    """Additive masks: a row whose keys are all masked attends uniformly (the reference's behaviour, not NaN)."""
+def test_attention_fully_masked_row_is_finite(eng):
+    """Additive masks: a row whose keys are all masked still attends by its raw scores (the reference's behaviour, not NaN)."""
     g = torch.Generator().manual_seed(5)
     q, k, v = (torch.randn(1, 4, 128, generator=g) for _ in range(3))
     mask = torch.zeros(1, 4)
@@ -134,7 +134,6 @@ def test_attention_fully_masked_row_is_uniform(eng):
     ref = _ref_attention(q, k, v, 2, mask, -10000.0, False)
     # adding -10000 in fp32 quantises the scores to ~1e-3 (the reference's fp32 arithmetic does the same), hence the tolerance
     assert torch.isfinite(y).all() and max_abs(y, ref) < 5e-3
-    assert max_abs(y, v.mean(1, keepdim=True).expand_as(y)) < 0.2
 
 
 @pytest.mark.parametrize("B,K", [(3, 5), (2, 1), (4, 2)])
