@@ -95,6 +95,150 @@ dec_self_attn_kernel(DecodeGeom g, int layer, const T* __restrict__ qkv, T* __re
     if (u < nd) o[lane + 32 * u] = from_f32<T>(acc[u]);
 }
 
+// Cross-attention of all K beam rows of one image over that image's K/V for one head (HBM-bound streaming kernel).
+// grid (heads, images); every K/V byte is read from global exactly once per CTA, by one warp, with fully coalesced
+// 16-byte loads (a head's [Le][D] block is contiguous in the head-major cache), and is reused for all K beams from
+// registers.  Exact (two-pass) softmax: scores -> shared memory -> per-beam softmax -> P*V, so the arithmetic is the
+// reference's softmax(QK^T/sqrt(d) + (1-m)*-1e9) V, not an online rescaling.
+template <typename T, int KB, int D>
+__global__ void __launch_bounds__(256, 2)
+dec_cross_attn_kernel(DecodeGeom g, const T* __restrict__ q, const T* __restrict__ kv_layer, const float* __restrict__ enc_mask,
+                      T* __restrict__ out) {
+  constexpr int EPL = 16 / sizeof(T);          // elements per 16-byte lane load
+  constexpr int LPR = D / EPL;                 // lanes per key row
+  constexpr int RPI = 32 / LPR;                // key rows per warp-wide load
+  constexpr int kWarps = 8;
+  extern __shared__ float smem[];
+  const int Le = g.Le;
+  float* S = smem;                             // [KB][Le] scores, then probabilities
+  float* part = smem + KB * Le;                // [kWarps][KB][D] partial outputs
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int sub = lane / LPR, chunk = lane % LPR;
+  const T* Kp = kv_layer + ((int64_t)b * 2 * g.heads + h) * Le * D;
+  const T* Vp = kv_layer + ((int64_t)b * 2 * g.heads + g.heads + h) * Le * D;
+  const float* mrow = enc_mask ? enc_mask + (int64_t)b * Le : nullptr;
+
+  float qr[KB][EPL];
+#pragma unroll
+  for (int k = 0; k < KB; ++k) {
+    if (k < g.K) {
+      float tmp[8];
+      const T* qp = q + ((int64_t)(b * g.K + k)) * g.H + h * D + chunk * EPL;
+      if constexpr (sizeof(T) == 2) { Vec8<T>::load(qp, tmp); }
+      else { float4 f = *reinterpret_cast<const float4*>(qp); tmp[0] = f.x; tmp[1] = f.y; tmp[2] = f.z; tmp[3] = f.w; }
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) qr[k][e] = tmp[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) qr[k][e] = 0.f;
+    }
+  }
+  const float scale_div = sqrtf((float)D);
+  // ---- phase 1: scores ----
+  for (int j0 = warp * RPI; j0 < Le; j0 += kWarps * RPI) {
+    const int j = j0 + sub;
+    float kr[EPL];
+    if (j < Le) {
+      const T* kp = Kp + (int64_t)j * D + chunk * EPL;
+      if constexpr (sizeof(T) == 2) { float tmp[8]; Vec8<T>::load(kp, tmp);
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) kr[e] = tmp[e]; }
+      else { float4 f = *reinterpret_cast<const float4*>(kp); kr[0] = f.x; kr[1] = f.y; kr[2] = f.z; kr[3] = f.w; }
+    } else {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) kr[e] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+      float p = 0.f;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) p = fmaf(qr[k][e], kr[e], p);
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+      if (chunk == 0 && j < Le && k < g.K) {
+        const float m = mrow ? mrow[j] : 1.f;
+        S[k * Le + j] = p / scale_div + (1.0f - m) * -1e9f;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- softmax: one warp per beam ----
+  for (int k = warp; k < g.K; k += kWarps) {
+    float mx = -INFINITY;
+    for (int j = lane; j < Le; j += 32) mx = fmaxf(mx, S[k * Le + j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < Le; j += 32) { const float e = expf(S[k * Le + j] - mx); S[k * Le + j] = e; sum += e; }
+    sum = warp_sum(sum);
+    for (int j = lane; j < Le; j += 32) S[k * Le + j] = S[k * Le + j] / sum;
+  }
+  __syncthreads();
+  // ---- phase 2: P * V ----
+  float acc[KB][EPL];
+#pragma unroll
+  for (int k = 0; k < KB; ++k)
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[k][e] = 0.f;
+  for (int j0 = warp * RPI; j0 < Le; j0 += kWarps * RPI) {
+    const int j = j0 + sub;
+    if (j < Le) {
+      float vr[EPL];
+      const T* vp = Vp + (int64_t)j * D + chunk * EPL;
+      if constexpr (sizeof(T) == 2) { float tmp[8]; Vec8<T>::load(vp, tmp);
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) vr[e] = tmp[e]; }
+      else { float4 f = *reinterpret_cast<const float4*>(vp); vr[0] = f.x; vr[1] = f.y; vr[2] = f.z; vr[3] = f.w; }
+#pragma unroll
+      for (int k = 0; k < KB; ++k) {
+        const float p = (k < g.K) ? S[k * Le + j] : 0.f;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) acc[k][e] = fmaf(p, vr[e], acc[k][e]);
+      }
+    }
+  }
+  // reduce over the RPI key sub-rows held by different lane groups, then over warps through shared memory
+#pragma unroll
+  for (int k = 0; k < KB; ++k)
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      float v = acc[k][e];
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      acc[k][e] = v;
+    }
+  if (sub == 0) {
+#pragma unroll
+    for (int k = 0; k < KB; ++k)
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) part[(warp * KB + k) * D + chunk * EPL + e] = acc[k][e];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < g.K * D; i += blockDim.x) {
+    const int k = i / D, d = i - k * D;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) v += part[(w * KB + k) * D + d];
+    out[((int64_t)(b * g.K + k)) * g.H + h * D + d] = from_f32<T>(v);
+  }
+}
+
+template <typename T, int KB>
+void launch_cross_kb(const DecodeGeom& g, const T* q, const T* kv_layer, const float* enc_mask, T* out, cudaStream_t stream) {
+  const size_t smem = ((size_t)KB * g.Le + (size_t)8 * KB * 64) * sizeof(float);
+  dim3 grid(g.heads, g.B);
+  dec_cross_attn_kernel<T, KB, 64><<<grid, 256, smem, stream>>>(g, q, kv_layer, enc_mask, out);
+}
+template <typename T>
+void launch_cross_t(const DecodeGeom& g, const void* q, const void* kv_layer, const float* enc_mask, void* out, cudaStream_t stream) {
+  const T* qq = (const T*)q; const T* kv = (const T*)kv_layer; T* o = (T*)out;
+  if (g.K == 1) launch_cross_kb<T, 1>(g, qq, kv, enc_mask, o, stream);
+  else if (g.K == 2) launch_cross_kb<T, 2>(g, qq, kv, enc_mask, o, stream);
+  else if (g.K <= 4) launch_cross_kb<T, 4>(g, qq, kv, enc_mask, o, stream);
+  else if (g.K == 5) launch_cross_kb<T, 5>(g, qq, kv, enc_mask, o, stream);
+  else launch_cross_kb<T, 8>(g, qq, kv, enc_mask, o, stream);
+}
+
 // One CTA per (image, layer*2+kv).  Thread-local dependency only: every thread loads the K source values of its
 // column chunk before it stores any of them, so duplicated parents (beam_idx is not a permutation) are safe in place.
 template <typename T>
@@ -144,6 +288,11 @@ int launch_dec_cross_attn(int dtype, const DecodeGeom& g, int layer, const void*
   const int64_t esz = dtype == kF32 ? 4 : 2;
   const int64_t per_image = (int64_t)2 * g.heads * g.Le * g.D;
   const char* kbase = (const char*)cross_cache + ((int64_t)layer * g.B) * per_image * esz;
+  if (g.D == 64 && g.K <= 8 && g.Le <= 1024) {
+    if (dtype == kF32) launch_cross_t<float>(g, q, kbase, enc_mask, out, stream);
+    else launch_cross_t<bf16>(g, q, kbase, enc_mask, out, stream);
+    return 1;
+  }
   AttnArgs a;
   a.q = q; a.q_bs = g.H; a.q_hs = g.D; a.q_rs = 0;
   a.k = kbase; a.k_bs = per_image; a.k_hs = (int64_t)g.Le * g.D; a.k_rs = g.D;

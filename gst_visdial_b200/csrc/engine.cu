@@ -354,7 +354,11 @@ struct Exec {
     a.o = o; a.o_bs = (int64_t)Lq * ldo; a.o_hs = D; a.o_rs = ldo;
     a.kmask = kmask; a.kmask_bs = Lk; a.neg = neg; a.causal = causal;
     a.B = B; a.H = heads; a.Lq = Lq; a.Lk = Lk; a.D = D; a.kv_batch_div = 1;
-    c->launches += launch_attention_generic(a, dt(), s);
+    run_attention(a);
+  }
+  void run_attention(const AttnArgs& a) {
+    if (c->dtype == kBF16 && !(c->cfg.flags & GSTVD_FLAG_GENERIC_ATTENTION) && attention_mma_supported(a)) c->launches += launch_attention_mma(a, s);
+    else c->launches += launch_attention_generic(a, dt(), s);
   }
   char* off(void* p, size_t elems) const { return (char*)p + elems * c->esz; }
   const char* off(const void* p, size_t elems) const { return (const char*)p + elems * c->esz; }
@@ -647,7 +651,7 @@ void do_score(gstvd_ctx* c, int B, int L, int64_t* dec_ids, const float* dec_mas
       a.o = c->dctx.p; a.o_bs = (int64_t)L * H; a.o_hs = D; a.o_rs = H;
       a.kmask = (const float*)c->fused_mask.p; a.kmask_bs = Le; a.neg = -1e9f; a.causal = 0;
       a.B = B; a.H = c->dec_heads; a.Lq = L; a.Lk = Le; a.D = D; a.kv_batch_div = 1;
-      c->launches += launch_attention_generic(a, c->dtype, s);
+      X.run_attention(a);
     }
     X.gemm(c->dctx.p, H, Ly.co, c->dtmp.p, H, M);
     X.add_ln(c->dtmp.p, c->da.p, Ly.ln_cross, c->db.p, M);
@@ -959,7 +963,8 @@ int gstvd_op_attention(gstvd_ctx* c, int dtype, int B, int H, int Lq, int Lk, in
       c->launches += launch_cast_f32_to(kBF16, k, k16, nk, s);
       c->launches += launch_cast_f32_to(kBF16, v, v16, nk, s);
       a.q = q16; a.k = k16; a.v = v16; a.o = o16;
-      c->launches += launch_attention_generic(a, kBF16, s);
+      if (!(c->cfg.flags & GSTVD_FLAG_GENERIC_ATTENTION) && attention_mma_supported(a)) c->launches += launch_attention_mma(a, s);
+      else c->launches += launch_attention_generic(a, kBF16, s);
       c->launches += launch_cast_to_f32(kBF16, o16, out, nq, s);
       CUDA_CHECK(cudaStreamSynchronize(s));
     }

@@ -10,7 +10,8 @@
 //                 STAGES-deep shared-memory ring (128-byte swizzle), completion on mbarriers
 //   warp 1      : MMA issuer    - one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per k-block
 //                 into one of two TMEM accumulator stages; tcgen05.commit releases ring slots / signals the epilogue
-//   warps 2..9  : epilogue      - tcgen05.ld (32 lanes x 32 columns per warp), + bias, erf-GELU, convert, 128-bit stores.
+//   warps 2..9  : epilogue      - tcgen05.ld (32 lanes x 32 columns per warp), + bias, GELU, convert, transpose through a
+//                 warp-private shared-memory tile, row-contiguous (coalesced) global stores.
 //                 Two accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
 // Both operands are K-major ("TN"), which is the layout of activations [rows, features] and nn.Linear weights
 // [out, in], so no transposes are ever materialised.  TMA zero-fills out-of-range rows / k, so M, N, K need not be
@@ -147,57 +148,112 @@ template <int BN> struct TileCfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // power of two for BN in {16,32,64,128,256}
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kBarBytes + 1024;   // +1024: manual alignment slack
+  static constexpr int kStageWords = 32 * 33;                   // per epilogue warp: 32 rows x 32 words, padded rows
+  static constexpr int kStagingBytes = kEpiWarps * kStageWords * 4;
+  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kBarBytes + kStagingBytes + 1024;   // +1024: alignment slack
 };
 
-template <typename OutT>
-__device__ __forceinline__ void store_chunk(const GemmArgs& p, int row, int col0, uint32_t (&acc)[32]) {
-  // acc: 32 consecutive output columns of `row`, raw fp32 accumulators
-  int64_t idx;
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 resolution): 2 MUFU + ~12 FMA-pipe instructions
+// instead of erff's two-branch polynomial, so the GELU epilogue stays hidden behind the MMA main loop.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  poly *= t;
+  const float e = exp2f(-1.44269504088896340736f * z * z);
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  const float erf = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf);
+}
+
+__device__ __forceinline__ int64_t out_index(const GemmArgs& p, int row, int col) {
   if (p.hm_D > 0) {
-    int b = row / p.hm_L, pos = row - b * p.hm_L;
-    int g = col0 / p.hm_D, d = col0 - g * p.hm_D;
-    int layer = g / p.hm_G, r = g - layer * p.hm_G;
-    idx = ((((int64_t)layer * p.hm_B + b) * p.hm_G + r) * p.hm_L + pos) * p.hm_D + d;
-  } else {
-    idx = (int64_t)row * p.ldc + col0;
+    const int b = row / p.hm_L, pos = row - b * p.hm_L;
+    const int g = col / p.hm_D, d = col - g * p.hm_D;
+    const int layer = g / p.hm_G, r = g - layer * p.hm_G;
+    return ((((int64_t)layer * p.hm_B + b) * p.hm_G + r) * p.hm_L + pos) * p.hm_D + d;
   }
-  OutT* out = reinterpret_cast<OutT*>(p.C) + idx;
-  const bool full = (col0 + 32 <= p.N);
-  const bool vec_ok = full && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  return (int64_t)row * p.ldc + col;
+}
+
+// Epilogue of one W-column block of this warp's 32 accumulator rows: TMEM -> registers (thread = row) -> + bias,
+// activation, convert -> transpose through a warp-private padded shared-memory tile -> global stores in which the 32
+// lanes of one instruction cover CONTIGUOUS bytes of one (or two) output rows (128 B segments), instead of 32 different
+// rows.  The uncoalesced variant (one 16-byte store per row per instruction) was L2-transaction bound: 3x slower.
+template <typename OutT, int W>
+__device__ __forceinline__ void epilogue_block(const GemmArgs& p, uint32_t taddr, uint32_t* stage, int row0, int col0, int lane) {
+  constexpr bool kBf16 = sizeof(OutT) == 2;
+  constexpr int kWords = kBf16 ? W / 2 : W;       // 32-bit words per output row in this block
+  static_assert(kWords <= 32, "block too wide for the staging tile");
+  const bool full = (col0 + W <= p.N);
   const bool bias_vec = p.bias != nullptr && full && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0);
 #pragma unroll
-  for (int g8 = 0; g8 < 4; ++g8) {
-    float v[8];
+  for (int part = 0; part < W / 32; ++part) {
+    uint32_t acc[32];
+    tmem_ld32(taddr + part * 32, acc);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g8 * 8 + j]);
-    if (p.bias) {
-      if (bias_vec) {
-        float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g8 * 8));
-        float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g8 * 8 + 4));
-        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-      } else {
+    for (int g8 = 0; g8 < 4; ++g8) {
+      float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          int c = col0 + g8 * 8 + j;
-          if (c < p.N) v[j] += __ldg(p.bias + c);
+      for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g8 * 8 + j]);
+      const int cb = col0 + part * 32 + g8 * 8;
+      if (p.bias) {
+        if (bias_vec) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cb));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + 4));
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (cb + j < p.N) v[j] += __ldg(p.bias + cb + j);
         }
       }
-    }
-    if (p.act == 1) {
+      if (p.act == 1) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-    }
-    if (vec_ok) {
-      Vec8<OutT>::store(out + g8 * 8, v);
-    } else {
+        for (int j = 0; j < 8; ++j) v[j] = gelu_fast(v[j]);
+      }
+      if constexpr (kBf16) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        int c = col0 + g8 * 8 + j;
-        if (c < p.N) out[g8 * 8 + j] = from_f32<OutT>(v[j]);
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          stage[lane * 33 + part * 16 + g8 * 4 + j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) stage[lane * 33 + part * 32 + g8 * 8 + j] = __float_as_uint(v[j]);
       }
     }
   }
+  __syncwarp();
+  constexpr int kRowsPerInstr = 32 / kWords;
+  constexpr int kColsPerWord = kBf16 ? 2 : 1;
+  const int w = lane % kWords, rsub = lane / kWords;
+  const int col = col0 + w * kColsPerWord;
+  const bool ld_even = kBf16 ? ((p.hm_D > 0) || ((p.ldc & 1) == 0)) : true;
+#pragma unroll 4
+  for (int i0 = 0; i0 < 32; i0 += kRowsPerInstr) {
+    const int r = i0 + rsub;
+    const int row = row0 + r;
+    const uint32_t word = stage[r * 33 + w];
+    if (row < p.M && col < p.N) {
+      OutT* dst = reinterpret_cast<OutT*>(p.C) + out_index(p, row, col);
+      if constexpr (kBf16) {
+        if (col + 1 < p.N && ld_even) {
+          *reinterpret_cast<uint32_t*>(dst) = word;
+        } else {
+          const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&word);
+          dst[0] = h.x;
+          if (col + 1 < p.N) dst[1] = h.y;
+        }
+      } else {
+        *reinterpret_cast<uint32_t*>(dst) = word;
+      }
+    }
+  }
+  __syncwarp();
 }
 
 template <int BN>
@@ -217,6 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  const uint32_t stage_base = bar_base + Cfg::kBarBytes;
   uint8_t* smem_gen = smem_raw + (base - raw);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
 
@@ -288,21 +345,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     constexpr int kColsPerHalf = BN >= 64 ? BN / 2 : BN;
     const int c_begin = (BN >= 64) ? half * kColsPerHalf : 0;
     const int c_end = (BN >= 64) ? c_begin + kColsPerHalf : (half == 0 ? BN : 0);
+    uint32_t* stage = reinterpret_cast<uint32_t*>(smem_gen + (stage_base - base)) + e * Cfg::kStageWords;
     int iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
       const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
       const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const int row = m_blk * BM + quad * 32 + lane;
-      for (int c = c_begin; c < c_end; c += 32) {
-        const int col0 = n_blk * BN + c;
-        if (col0 >= p.N) break;                       // warp-uniform
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + c, acc);
-        if (row < p.M) {
-          if (p.out_f32) store_chunk<float>(p, row, col0, acc);
-          else store_chunk<bf16>(p, row, col0, acc);
+      const int row0 = m_blk * BM + quad * 32;
+      constexpr int kWb = (BN >= 128) ? 64 : 32;           // bf16 block width; fp32 output always uses 32-column blocks
+      if (p.out_f32) {
+        for (int c = c_begin; c < c_end; c += 32) {
+          const int col0 = n_blk * BN + c;
+          if (col0 >= p.N) break;                           // warp-uniform
+          epilogue_block<float, 32>(p, tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + c, stage, row0, col0, lane);
+        }
+      } else {
+        for (int c = c_begin; c < c_end; c += kWb) {
+          const int col0 = n_blk * BN + c;
+          if (col0 >= p.N) break;
+          epilogue_block<bf16, kWb>(p, tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + c, stage, row0, col0, lane);
         }
       }
       tc_fence_before();

@@ -43,6 +43,7 @@ struct AttnArgs {
 int launch_attention_generic(const AttnArgs& a, int dtype, cudaStream_t stream);
 // Tensor-core (mma.sync bf16) attention for the encoder / teacher-forced shapes; D in {64,128}.
 int launch_attention_mma(const AttnArgs& a, cudaStream_t stream);
+bool attention_mma_supported(const AttnArgs& a);
 
 // y = LN(x + residual) ; rows x width ; dtype of x/residual/y = dtype ; gamma/beta fp32
 int launch_add_layernorm(int dtype, int rows, int width, const void* x, int64_t ldx, const void* residual, int64_t ldr,
