@@ -100,6 +100,20 @@ dec_self_attn_kernel(DecodeGeom g, int layer, const T* __restrict__ qkv, T* __re
 // 16-byte loads (a head's [Le][D] block is contiguous in the head-major cache), and is reused for all K beams from
 // registers.  Exact (two-pass) softmax: scores -> shared memory -> per-beam softmax -> P*V, so the arithmetic is the
 // reference's softmax(QK^T/sqrt(d) + (1-m)*-1e9) V, not an online rescaling.
+template <typename T> struct Raw16 {};
+template <> struct Raw16<bf16> {
+  static __device__ __forceinline__ void unpack(const uint4& r, float (&o)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+  }
+};
+template <> struct Raw16<float> {
+  static __device__ __forceinline__ void unpack(const uint4& r, float (&o)[4]) {
+    o[0] = __uint_as_float(r.x); o[1] = __uint_as_float(r.y); o[2] = __uint_as_float(r.z); o[3] = __uint_as_float(r.w);
+  }
+};
+
 template <typename T, int KB, int D>
 __global__ void __launch_bounds__(256, 2)
 dec_cross_attn_kernel(DecodeGeom g, const T* __restrict__ q, const T* __restrict__ kv_layer, const float* __restrict__ enc_mask,
@@ -108,59 +122,70 @@ dec_cross_attn_kernel(DecodeGeom g, const T* __restrict__ q, const T* __restrict
   constexpr int LPR = D / EPL;                 // lanes per key row
   constexpr int RPI = 32 / LPR;                // key rows per warp-wide load
   constexpr int kWarps = 8;
+  constexpr int NIT = 10;                      // loads in flight per lane and operand: 8 warps x RPI x 10 keys per pass
+  constexpr int kPass = kWarps * RPI * NIT;
   extern __shared__ float smem[];
   const int Le = g.Le;
   float* S = smem;                             // [KB][Le] scores, then probabilities
   float* part = smem + KB * Le;                // [kWarps][KB][D] partial outputs
+  float* qs = part + kWarps * KB * D;          // [KB][D] queries (fp32)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, b = blockIdx.y;
   const int sub = lane / LPR, chunk = lane % LPR;
   const T* Kp = kv_layer + ((int64_t)b * 2 * g.heads + h) * Le * D;
   const T* Vp = kv_layer + ((int64_t)b * 2 * g.heads + g.heads + h) * Le * D;
   const float* mrow = enc_mask ? enc_mask + (int64_t)b * Le : nullptr;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
 
-  float qr[KB][EPL];
+  // K loads of the first pass are issued before anything else so that their latency overlaps the query staging
+  uint4 kreg[NIT];
 #pragma unroll
-  for (int k = 0; k < KB; ++k) {
-    if (k < g.K) {
-      float tmp[8];
-      const T* qp = q + ((int64_t)(b * g.K + k)) * g.H + h * D + chunk * EPL;
-      if constexpr (sizeof(T) == 2) { Vec8<T>::load(qp, tmp); }
-      else { float4 f = *reinterpret_cast<const float4*>(qp); tmp[0] = f.x; tmp[1] = f.y; tmp[2] = f.z; tmp[3] = f.w; }
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) qr[k][e] = tmp[e];
-    } else {
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) qr[k][e] = 0.f;
-    }
+  for (int it = 0; it < NIT; ++it) {
+    const int j = (it * kWarps + warp) * RPI + sub;
+    kreg[it] = (j < Le) ? *reinterpret_cast<const uint4*>(Kp + (int64_t)j * D + chunk * EPL) : zero4;
   }
+  for (int i = threadIdx.x; i < g.K * D; i += blockDim.x) {
+    const int k = i / D, d = i - k * D;
+    qs[k * D + d] = to_f32(q[((int64_t)(b * g.K + k)) * g.H + h * D + d]);
+  }
+  __syncthreads();
   const float scale_div = sqrtf((float)D);
   // ---- phase 1: scores ----
-  for (int j0 = warp * RPI; j0 < Le; j0 += kWarps * RPI) {
-    const int j = j0 + sub;
-    float kr[EPL];
-    if (j < Le) {
-      const T* kp = Kp + (int64_t)j * D + chunk * EPL;
-      if constexpr (sizeof(T) == 2) { float tmp[8]; Vec8<T>::load(kp, tmp);
+  for (int base = 0; base < Le; base += kPass) {
+    if (base > 0) {
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) kr[e] = tmp[e]; }
-      else { float4 f = *reinterpret_cast<const float4*>(kp); kr[0] = f.x; kr[1] = f.y; kr[2] = f.z; kr[3] = f.w; }
-    } else {
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) kr[e] = 0.f;
-    }
-#pragma unroll
-    for (int k = 0; k < KB; ++k) {
-      float p = 0.f;
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) p = fmaf(qr[k][e], kr[e], p);
-#pragma unroll
-      for (int o = LPR / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-      if (chunk == 0 && j < Le && k < g.K) {
-        const float m = mrow ? mrow[j] : 1.f;
-        S[k * Le + j] = p / scale_div + (1.0f - m) * -1e9f;
+      for (int it = 0; it < NIT; ++it) {
+        const int j = base + (it * kWarps + warp) * RPI + sub;
+        kreg[it] = (j < Le) ? *reinterpret_cast<const uint4*>(Kp + (int64_t)j * D + chunk * EPL) : zero4;
       }
     }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int j = base + (it * kWarps + warp) * RPI + sub;
+      float kr[EPL];
+      Raw16<T>::unpack(kreg[it], kr);
+#pragma unroll
+      for (int k = 0; k < KB; ++k) {
+        float p = 0.f;
+        if (k < g.K) {
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) p = fmaf(qs[k * D + chunk * EPL + e], kr[e], p);
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        if (chunk == 0 && j < Le && k < g.K) {
+          const float m = mrow ? mrow[j] : 1.f;
+          S[k * Le + j] = p / scale_div + (1.0f - m) * -1e9f;
+        }
+      }
+    }
+  }
+  // V loads of the first pass: in flight while the softmax runs
+  uint4 vreg[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int j = (it * kWarps + warp) * RPI + sub;
+    vreg[it] = (j < Le) ? *reinterpret_cast<const uint4*>(Vp + (int64_t)j * D + chunk * EPL) : zero4;
   }
   __syncthreads();
   // ---- softmax: one warp per beam ----
@@ -180,20 +205,26 @@ dec_cross_attn_kernel(DecodeGeom g, const T* __restrict__ q, const T* __restrict
   for (int k = 0; k < KB; ++k)
 #pragma unroll
     for (int e = 0; e < EPL; ++e) acc[k][e] = 0.f;
-  for (int j0 = warp * RPI; j0 < Le; j0 += kWarps * RPI) {
-    const int j = j0 + sub;
-    if (j < Le) {
-      float vr[EPL];
-      const T* vp = Vp + (int64_t)j * D + chunk * EPL;
-      if constexpr (sizeof(T) == 2) { float tmp[8]; Vec8<T>::load(vp, tmp);
+  for (int base = 0; base < Le; base += kPass) {
+    if (base > 0) {
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) vr[e] = tmp[e]; }
-      else { float4 f = *reinterpret_cast<const float4*>(vp); vr[0] = f.x; vr[1] = f.y; vr[2] = f.z; vr[3] = f.w; }
+      for (int it = 0; it < NIT; ++it) {
+        const int j = base + (it * kWarps + warp) * RPI + sub;
+        vreg[it] = (j < Le) ? *reinterpret_cast<const uint4*>(Vp + (int64_t)j * D + chunk * EPL) : zero4;
+      }
+    }
 #pragma unroll
-      for (int k = 0; k < KB; ++k) {
-        const float p = (k < g.K) ? S[k * Le + j] : 0.f;
+    for (int it = 0; it < NIT; ++it) {
+      const int j = base + (it * kWarps + warp) * RPI + sub;
+      if (j < Le) {
+        float vr[EPL];
+        Raw16<T>::unpack(vreg[it], vr);
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) acc[k][e] = fmaf(p, vr[e], acc[k][e]);
+        for (int k = 0; k < KB; ++k) {
+          const float p = (k < g.K) ? S[k * Le + j] : 0.f;
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) acc[k][e] = fmaf(p, vr[e], acc[k][e]);
+        }
       }
     }
   }
@@ -225,7 +256,7 @@ dec_cross_attn_kernel(DecodeGeom g, const T* __restrict__ q, const T* __restrict
 
 template <typename T, int KB>
 void launch_cross_kb(const DecodeGeom& g, const T* q, const T* kv_layer, const float* enc_mask, T* out, cudaStream_t stream) {
-  const size_t smem = ((size_t)KB * g.Le + (size_t)8 * KB * 64) * sizeof(float);
+  const size_t smem = ((size_t)KB * g.Le + (size_t)8 * KB * 64 + (size_t)KB * 64) * sizeof(float);
   dim3 grid(g.heads, g.B);
   dec_cross_attn_kernel<T, KB, 64><<<grid, 256, smem, stream>>>(g, q, kv_layer, enc_mask, out);
 }

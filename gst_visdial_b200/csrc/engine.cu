@@ -916,7 +916,17 @@ int gstvd_op_linear(gstvd_ctx* c, int dtype, int M, int N, int K, const float* a
       g.A = a16; g.W = w16;
       gemm_tc_init();
       if (c->cfg.flags & GSTVD_FLAG_DEBUG_SIMT_GEMM) c->launches += launch_gemm_simt(g, kBF16, s);
-      else c->launches += launch_gemm_tc(g, c->num_sms, s);
+      else {
+        const bool prof = c->profiling && c->prof_used < c->prof_pool.size();
+        if (prof) cudaEventRecord(c->prof_pool[c->prof_used].a, s);
+        c->launches += launch_gemm_tc(g, c->num_sms, s);
+        if (prof) {
+          auto& r = c->prof_pool[c->prof_used++];
+          cudaEventRecord(r.b, s);
+          r.flops = 2.0 * M * (double)N * K;
+          r.bytes = 2.0 * ((double)M * K + (double)N * K) + 4.0 * M * (double)N;
+        }
+      }
       CUDA_CHECK(cudaStreamSynchronize(s));
     }
   });

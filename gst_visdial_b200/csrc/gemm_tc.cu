@@ -18,6 +18,7 @@
 // multiples of the tile (K % 8 == 0 for the 16-byte stride rule).
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -83,6 +84,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -238,7 +255,7 @@ __device__ __forceinline__ void epilogue_block(const GemmArgs& p, uint32_t taddr
     const int r = i0 + rsub;
     const int row = row0 + r;
     const uint32_t word = stage[r * 33 + w];
-    if (row < p.M && col < p.N) {
+    if (row < p.M && col < p.N && p.dbg != 1) {
       OutT* dst = reinterpret_cast<OutT*>(p.C) + out_index(p, row, col);
       if constexpr (kBf16) {
         if (col + 1 < p.N && ld_even) {
@@ -256,9 +273,84 @@ __device__ __forceinline__ void epilogue_block(const GemmArgs& p, uint32_t taddr
   __syncwarp();
 }
 
+// Epilogue of one CW-column block for the 128 rows of a tile, through a TMA store.  The 4 warps of a half-group (128
+// threads, thread = accumulator row) convert their row to the output type, write it into a 128-row staging tile in the
+// TMA swizzle pattern (16-byte chunk index XOR row bits -> conflict-free st.shared.v4), and one thread issues
+// cp.async.bulk.tensor (global <- shared), which clips at the M / N edges.  ~2 instructions per output element instead of
+// ~28 for the register/shared transpose with per-row address arithmetic, so 8 epilogue warps keep up with the MMA.
+template <typename OutT, int CW>
+__device__ __forceinline__ void epilogue_tma_block(const GemmArgs& p, const CUtensorMap* tm_c, uint32_t taddr, uint32_t stage_addr,
+                                                   int tile_row0, int col0, int r, int hf, bool issuer) {
+  constexpr int kRowBytes = CW * (int)sizeof(OutT);     // 64 or 128
+  constexpr int kChunks = kRowBytes / 16;
+  constexpr int kWordsRow = kRowBytes / 4;
+  if (issuer) bulk_wait_read0();                        // the previous store out of this staging tile has been read
+  named_bar_sync(1 + hf, 128);
+  uint32_t packed[kWordsRow];
+  const bool full = (col0 + CW <= p.N);
+  const bool bias_vec = p.bias != nullptr && full && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0);
+#pragma unroll
+  for (int part = 0; part < CW / 32; ++part) {
+    uint32_t acc[32];
+    tmem_ld32(taddr + part * 32, acc);
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g8 * 8 + j]);
+      const int cb = col0 + part * 32 + g8 * 8;
+      if (p.bias) {
+        if (bias_vec) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cb));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + 4));
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (cb + j < p.N) v[j] += __ldg(p.bias + cb + j);
+        }
+      }
+      if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = gelu_fast(v[j]);
+      }
+      if constexpr (sizeof(OutT) == 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          packed[part * 16 + g8 * 4 + j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) packed[part * 32 + g8 * 8 + j] = __float_as_uint(v[j]);
+      }
+    }
+  }
+  const int sw = (kRowBytes == 128) ? (r & 7) : ((r >> 1) & 3);
+  const uint32_t row_addr = stage_addr + r * kRowBytes;
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c)
+    st_shared_v4(row_addr + ((c ^ sw) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+  fence_proxy_async();                                  // generic-proxy writes -> visible to the async (TMA) proxy
+  named_bar_sync(1 + hf, 128);
+  if (issuer && p.dbg != 1) {
+    if (p.hm_D > 0) {
+      // head-major scatter: column block = one (layer, k|v, head); rows = (image, position), possibly two images per tile
+      const int g = col0 / p.hm_D, layer = g / p.hm_G, rr = g - layer * p.hm_G;
+      int b = tile_row0 / p.hm_L;
+      for (; b < p.hm_B && b * p.hm_L < tile_row0 + BM; ++b)
+        tma_store_4d(tm_c, stage_addr, 0, tile_row0 - b * p.hm_L, rr, layer * p.hm_B + b);
+    } else {
+      tma_store_2d(tm_c, stage_addr, col0, tile_row0);
+    }
+    bulk_commit();
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmArgs p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+               const __grid_constant__ CUtensorMap tm_c, const GemmArgs p) {
   using Cfg = TileCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -266,14 +358,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const uint32_t base = (raw + 1023u) & ~1023u;                 // 128B-swizzle atoms need 1024-byte alignment
   const uint32_t a_base = base;
   const uint32_t b_base = base + kStages * Cfg::kABytes;
-  const uint32_t bar_base = b_base + kStages * Cfg::kBBytes;
+  const uint32_t stage_base = b_base + kStages * Cfg::kBBytes;   // epilogue staging (1024-byte aligned: TMA-store source)
+  const uint32_t bar_base = stage_base + Cfg::kStagingBytes;
   // barrier layout: full[kStages] | empty[kStages] | tmem_full[2] | tmem_empty[2] | tmem base address (u32)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
-  const uint32_t stage_base = bar_base + Cfg::kBarBytes;
   uint8_t* smem_gen = smem_raw + (base - raw);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
 
@@ -286,6 +378,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
+    if (p.tma_store) tma_prefetch_desc(&tm_c);
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps * 32); }
     fence_barrier_init();
@@ -329,7 +422,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (p.dbg != 3) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));             // frees the smem slot when these MMAs retire
           if (kb == num_kb - 1) umma_commit(tfull_bar(as));
@@ -353,8 +446,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const int row0 = m_blk * BM + quad * 32;
+      if (p.dbg == 2) { tc_fence_before(); mbar_arrive(tempty_bar(as)); continue; }
       constexpr int kWb = (BN >= 128) ? 64 : 32;           // bf16 block width; fp32 output always uses 32-column blocks
-      if (p.out_f32) {
+      if (p.tma_store) {
+        const int r = quad * 32 + lane;                     // accumulator row == TMEM lane == staging row
+        const bool issuer = (e == half * 4) && lane == 0;
+        const uint32_t stg = stage_base + half * 16384;
+        const uint32_t tq = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+        if (p.out_f32) {
+          for (int j = half; j < BN / 32; j += 2) {
+            const int col0 = n_blk * BN + j * 32;
+            if (col0 >= p.N) break;                         // uniform across the half-group
+            epilogue_tma_block<float, 32>(p, &tm_c, tq + j * 32, stg, m_blk * BM, col0, r, half, issuer);
+          }
+        } else {
+          for (int j = half; j < BN / kWb; j += 2) {
+            const int col0 = n_blk * BN + j * kWb;
+            if (col0 >= p.N) break;
+            epilogue_tma_block<bf16, kWb>(p, &tm_c, tq + j * kWb, stg, m_blk * BM, col0, r, half, issuer);
+          }
+        }
+      } else if (p.out_f32) {
         for (int c = c_begin; c < c_end; c += 32) {
           const int col0 = n_blk * BN + c;
           if (col0 >= p.N) break;                           // warp-uniform
@@ -370,6 +482,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       tc_fence_before();
       mbar_arrive(tempty_bar(as));
     }
+    if (p.tma_store && (e & 3) == 0 && lane == 0) bulk_wait0();   // outstanding TMA stores must finish before smem goes away
   }
   tc_fence_before();
   __syncthreads();
@@ -384,43 +497,69 @@ EncodeTiledFn g_encode = nullptr;
 std::once_flag g_once;
 
 struct MapKey {
-  const void* ptr; int64_t rows, cols, ld; int box_rows;
-  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
+  const void* ptr; int64_t rows, cols, ld; int box_rows, box_cols, esz, kind; int64_t d2, d3;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols &&
+           esz == o.esz && kind == o.kind && d2 == o.d2 && d3 == o.d3;
+  }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
-    h = h * 1000003u ^ static_cast<size_t>(k.rows); h = h * 1000003u ^ static_cast<size_t>(k.cols);
-    h = h * 1000003u ^ static_cast<size_t>(k.ld); h = h * 1000003u ^ static_cast<size_t>(k.box_rows);
+    for (int64_t v : {k.rows, k.cols, k.ld, (int64_t)k.box_rows, (int64_t)k.box_cols, (int64_t)k.esz, (int64_t)k.kind, k.d2, k.d3})
+      h = h * 1000003u ^ static_cast<size_t>(v);
     return h;
   }
 };
 std::mutex g_map_mu;
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
-// 2-D bf16 tensor [rows, cols] with row stride ld (elements); box = 64 columns x box_rows rows, 128-byte swizzle.
-const CUtensorMap& get_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
-  MapKey key{ptr, rows, cols, ld, box_rows};
+const CUtensorMap& cached_map(const MapKey& key, CUtensorMapDataType dt, int rank, const cuuint64_t* gdim, const cuuint64_t* gstride,
+                              const cuuint32_t* box, CUtensorMapSwizzle swz) {
   std::lock_guard<std::mutex> lk(g_map_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) return it->second;
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0)
-    throw std::runtime_error("gemm_tc: operand must be 16-byte aligned with a row stride that is a multiple of 8 elements");
   CUtensorMap m;
-  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld * 2)};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(&m, dt, rank, const_cast<void*>(key.ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   if (g_maps.size() > 4096) g_maps.clear();
   return g_maps.emplace(key, m).first->second;
 }
 
+// 2-D bf16 operand [rows, cols] with row stride ld (elements); box = 64 columns x box_rows rows, 128-byte swizzle.
+const CUtensorMap& get_map(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0)
+    throw std::runtime_error("gemm_tc: operand must be 16-byte aligned with a row stride that is a multiple of 8 elements");
+  MapKey key{ptr, rows, cols, ld, box_rows, BK, 2, 0, 0, 0};
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld * 2)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  return cached_map(key, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+// Output map for the TMA-store epilogue: [M, N] row-major with box = box_cols x 128 rows.
+const CUtensorMap& get_map_c(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int esz, int box_cols) {
+  MapKey key{ptr, rows, cols, ld, BM, box_cols, esz, 1, 0, 0};
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld * esz)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(BM)};
+  return cached_map(key, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, gdim, gstride, box,
+                    box_cols * esz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+// Head-major cross-KV output [layers*B][G][L][D] bf16 (GemmArgs::hm_*): box = D x 128 positions of one (layer-image, group).
+const CUtensorMap& get_map_hm(const void* ptr, int D, int L, int G, int64_t LB) {
+  MapKey key{ptr, L, D, D, BM, D, 2, 2, G, LB};
+  cuuint64_t gdim[4] = {(cuuint64_t)D, (cuuint64_t)L, (cuuint64_t)G, (cuuint64_t)LB};
+  cuuint64_t gstride[3] = {(cuuint64_t)D * 2, (cuuint64_t)L * D * 2, (cuuint64_t)G * L * D * 2};
+  cuuint32_t box[4] = {(cuuint32_t)D, (cuuint32_t)BM, 1, 1};
+  return cached_map(key, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 template <int BN>
-void launch_cfg(const GemmArgs& a, int num_sms, cudaStream_t stream) {
+void launch_cfg(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -428,11 +567,26 @@ void launch_cfg(const GemmArgs& a, int num_sms, cudaStream_t stream) {
     if (e != cudaSuccess) throw std::runtime_error(std::string("gemm_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     attr_set = true;
   }
+  GemmArgs a = a_in;
   const CUtensorMap& ma = get_map(a.A, a.M, a.K, a.lda, BM);
   const CUtensorMap& mb = get_map(a.W, a.N, a.K, a.ldw, BN);
+  // TMA-store epilogue when the output is expressible as a tensor map; otherwise the generic register/shared path
+  const int esz = a.out_f32 ? 4 : 2;
+  const int cw = a.out_f32 ? 32 : (BN >= 128 ? 64 : 32);
+  const CUtensorMap* mc = &ma;
+  a.tma_store = 0;
+  static const bool no_tma_store = getenv("GSTVD_GEMM_NO_TMA_STORE") != nullptr;
+  if (!no_tma_store && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0) {
+    if (a.hm_D > 0) {
+      if (!a.out_f32 && cw == a.hm_D && a.hm_D == 64) { mc = &get_map_hm(a.C, a.hm_D, a.hm_L, a.hm_G, (int64_t)(a.N / (a.hm_D * a.hm_G)) * a.hm_B); a.tma_store = 1; }
+    } else if ((a.ldc * esz) % 16 == 0) {
+      mc = &get_map_c(a.C, a.M, a.N, a.ldc, esz, cw);
+      a.tma_store = 1;
+    }
+  }
   const int tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_tc_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ma, mb, a);
+  gemm_tc_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ma, mb, *mc, a);
 }
 
 }  // namespace
@@ -448,8 +602,12 @@ void gemm_tc_init() {
   });
 }
 
-int launch_gemm_tc(const GemmArgs& a, int num_sms, cudaStream_t stream) {
-  if (a.M <= 0 || a.N <= 0) return 0;
+int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
+  if (a_in.M <= 0 || a_in.N <= 0) return 0;
+  static const int dbg_env = [] { const char* e = getenv("GSTVD_GEMM_DBG"); return e ? atoi(e) : 0; }();
+  static const int bn_env = [] { const char* e = getenv("GSTVD_GEMM_BN"); return e ? atoi(e) : 0; }();
+  GemmArgs a = a_in;
+  a.dbg = dbg_env;
   if (a.K % 8 != 0) throw std::runtime_error("gemm_tc: K must be a multiple of 8");
   if (a.hm_D > 0 && (a.hm_D % 32 != 0)) throw std::runtime_error("gemm_tc: head-major scatter needs head_dim % 32 == 0");
   gemm_tc_init();
@@ -460,6 +618,7 @@ int launch_gemm_tc(const GemmArgs& a, int num_sms, cudaStream_t stream) {
   for (int i = 0; i < 3; ++i) {
     if (a.N >= cand[i] && tiles_m * ((a.N + cand[i] - 1) / cand[i]) >= num_sms) { bn = cand[i]; break; }
   }
+  if (bn_env) bn = bn_env;
   switch (bn) {
     case 256: launch_cfg<256>(a, num_sms, stream); break;
     case 128: launch_cfg<128>(a, num_sms, stream); break;
