@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -914,6 +915,9 @@ int gstvd_op_linear(gstvd_ctx* c, int dtype, int M, int N, int K, const float* a
       c->launches += launch_cast_f32_to(kBF16, a, a16, (int64_t)M * K, s);
       c->launches += launch_cast_f32_to(kBF16, w, w16, (int64_t)N * K, s);
       g.A = a16; g.W = w16;
+      static const bool bf16_out = getenv("GSTVD_OP_LINEAR_BF16OUT") != nullptr;   // measurement aid: time the bf16-output epilogue
+      void* c16 = nullptr;
+      if (bf16_out) { c16 = sc.get((size_t)M * N * 2); g.C = c16; g.out_f32 = 0; }
       gemm_tc_init();
       if (c->cfg.flags & GSTVD_FLAG_DEBUG_SIMT_GEMM) c->launches += launch_gemm_simt(g, kBF16, s);
       else {
@@ -927,6 +931,7 @@ int gstvd_op_linear(gstvd_ctx* c, int dtype, int M, int N, int K, const float* a
           r.bytes = 2.0 * ((double)M * K + (double)N * K) + 4.0 * M * (double)N;
         }
       }
+      if (c16) c->launches += launch_cast_to_f32(kBF16, c16, out, (int64_t)M * N, s);
       CUDA_CHECK(cudaStreamSynchronize(s));
     }
   });

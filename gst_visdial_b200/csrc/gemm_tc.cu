@@ -34,7 +34,7 @@ namespace {
 constexpr int BM = 128;          // rows per tile  (UMMA M)
 constexpr int BK = 64;           // k per stage: 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;         // 4 per TMEM lane quadrant: the epilogue is ALU/latency bound, it needs the warps
 constexpr int kThreads = (2 + kEpiWarps) * 32;
 constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;   // 4 s: far beyond any legitimate wait
 
@@ -82,6 +82,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -94,6 +100,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -166,21 +176,22 @@ template <int BN> struct TileCfg {
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // power of two for BN in {16,32,64,128,256}
   static constexpr int kBarBytes = 256;
   static constexpr int kStageWords = 32 * 33;                   // per epilogue warp: 32 rows x 32 words, padded rows
-  static constexpr int kStagingBytes = kEpiWarps * kStageWords * 4;
+  static constexpr int kStagingBytes = 8 * kStageWords * 4;    // 33 KB: 4 x 8 KB (bf16) / 2 x 16 KB (fp32) TMA-store tiles, or 8 generic tiles
   static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kBarBytes + kStagingBytes + 1024;   // +1024: alignment slack
 };
 
-// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 resolution): 2 MUFU + ~12 FMA-pipe instructions
-// instead of erff's two-branch polynomial, so the GELU epilogue stays hidden behind the MMA main loop.
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.25 (|error| <= 2.5e-5, two orders of magnitude below
+// bf16 resolution) and approximate MUFU reciprocal / exp2: ~15 instructions per element instead of erff's ~35, so the GELU
+// epilogue of the FFN1 GEMM hides behind the MMA main loop.  (The fp32 parity path uses the exact erff in gemm_simt.cu.)
 __device__ __forceinline__ float gelu_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.47047f, z, 1.0f)));
+  float poly = fmaf(t, 0.7478556f, -0.0958798f);
+  poly = fmaf(t, poly, 0.3480242f);
   poly *= t;
-  const float e = exp2f(-1.44269504088896340736f * z * z);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.44269504088896340736f * z * z));
   const float erf_abs = fmaf(-poly, e, 1.0f);
   const float erf = copysignf(erf_abs, x);
   return 0.5f * x * (1.0f + erf);
@@ -280,12 +291,12 @@ __device__ __forceinline__ void epilogue_block(const GemmArgs& p, uint32_t taddr
 // ~28 for the register/shared transpose with per-row address arithmetic, so 8 epilogue warps keep up with the MMA.
 template <typename OutT, int CW>
 __device__ __forceinline__ void epilogue_tma_block(const GemmArgs& p, const CUtensorMap* tm_c, uint32_t taddr, uint32_t stage_addr,
-                                                   int tile_row0, int col0, int r, int hf, bool issuer) {
+                                                   int tile_row0, int col0, int r, int grp, bool issuer) {
   constexpr int kRowBytes = CW * (int)sizeof(OutT);     // 64 or 128
   constexpr int kChunks = kRowBytes / 16;
   constexpr int kWordsRow = kRowBytes / 4;
   if (issuer) bulk_wait_read0();                        // the previous store out of this staging tile has been read
-  named_bar_sync(1 + hf, 128);
+  named_bar_sync(1 + grp, 128);
   uint32_t packed[kWordsRow];
   const bool full = (col0 + CW <= p.N);
   const bool bias_vec = p.bias != nullptr && full && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0);
@@ -328,18 +339,26 @@ __device__ __forceinline__ void epilogue_tma_block(const GemmArgs& p, const CUte
   }
   const int sw = (kRowBytes == 128) ? (r & 7) : ((r >> 1) & 3);
   const uint32_t row_addr = stage_addr + r * kRowBytes;
+  if (p.dbg == 5) {                                     // measurement: keep the math alive without touching shared memory
+    uint32_t x = 0;
 #pragma unroll
-  for (int c = 0; c < kChunks; ++c)
-    st_shared_v4(row_addr + ((c ^ sw) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
-  fence_proxy_async();                                  // generic-proxy writes -> visible to the async (TMA) proxy
-  named_bar_sync(1 + hf, 128);
-  if (issuer && p.dbg != 1) {
+    for (int c = 0; c < kWordsRow; ++c) x ^= packed[c];
+    if (x == 0x12345678u) st_shared_v4(row_addr, x, x, x, x);
+  } else {
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c)
+      st_shared_v4(row_addr + ((c ^ sw) << 4), packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+  }
+  if (p.dbg != 5) fence_proxy_async();                  // generic-proxy writes -> visible to the async (TMA) proxy
+  named_bar_sync(1 + grp, 128);
+  if (issuer && p.dbg != 1 && p.dbg != 5) {
     if (p.hm_D > 0) {
-      // head-major scatter: column block = one (layer, k|v, head); rows = (image, position), possibly two images per tile
+      // head-major scatter: column block = one (layer, k|v, head); the M tiles of this mode never straddle two images
+      // (hm_tpi tiles per image, rows past hm_L are clipped by the store - TMA stores reject negative coordinates)
       const int g = col0 / p.hm_D, layer = g / p.hm_G, rr = g - layer * p.hm_G;
-      int b = tile_row0 / p.hm_L;
-      for (; b < p.hm_B && b * p.hm_L < tile_row0 + BM; ++b)
-        tma_store_4d(tm_c, stage_addr, 0, tile_row0 - b * p.hm_L, rr, layer * p.hm_B + b);
+      const int m_blk = tile_row0 / BM;
+      const int b = m_blk / p.hm_tpi, pos0 = (m_blk - b * p.hm_tpi) * BM;
+      tma_store_3d(tm_c, stage_addr, col0 - g * p.hm_D, pos0, (layer * p.hm_B + b) * p.hm_G + rr);
     } else {
       tma_store_2d(tm_c, stage_addr, col0, tile_row0);
     }
@@ -371,7 +390,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = (p.N + BN - 1) / BN;
-  const int tiles_m = (p.M + BM - 1) / BM;
+  const int tiles_m = p.hm_tpi > 0 ? p.hm_B * p.hm_tpi : (p.M + BM - 1) / BM;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (p.K + BK - 1) / BK;
 
@@ -398,7 +417,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), Cfg::kABytes + Cfg::kBBytes);
-          tma_load_2d(a_base + stage * Cfg::kABytes, &tm_a, kb * BK, m_blk * BM, full_bar(stage));
+          if (p.hm_tpi > 0) {
+            const int img = m_blk / p.hm_tpi;
+            tma_load_3d(a_base + stage * Cfg::kABytes, &tm_a, kb * BK, (m_blk - img * p.hm_tpi) * BM, img, full_bar(stage));
+          } else {
+            tma_load_2d(a_base + stage * Cfg::kABytes, &tm_a, kb * BK, m_blk * BM, full_bar(stage));
+          }
           tma_load_2d(b_base + stage * Cfg::kBBytes, &tm_b, kb * BK, n_blk * BN, full_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -434,11 +458,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // ---------------- epilogue ----------------
     const int e = warp - 2;
     const int quad = warp & 3;                        // TMEM lane quadrant this warp may access
-    const int half = e >> 2;                          // two warps per quadrant split the columns
+    const int grp = e >> 2;                           // 4 groups of 4 warps (one warp per quadrant = 128 accumulator rows)
+    const int half = grp;                             // the generic (non-TMA) path only uses groups 0 and 1
     constexpr int kColsPerHalf = BN >= 64 ? BN / 2 : BN;
     const int c_begin = (BN >= 64) ? half * kColsPerHalf : 0;
-    const int c_end = (BN >= 64) ? c_begin + kColsPerHalf : (half == 0 ? BN : 0);
-    uint32_t* stage = reinterpret_cast<uint32_t*>(smem_gen + (stage_base - base)) + e * Cfg::kStageWords;
+    const int c_end = (grp >= 2) ? 0 : ((BN >= 64) ? c_begin + kColsPerHalf : (half == 0 ? BN : 0));
+    uint32_t* stage = reinterpret_cast<uint32_t*>(smem_gen + (stage_base - base)) + (e & 7) * Cfg::kStageWords;
     int iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
       const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
@@ -447,23 +472,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       tc_fence_after();
       const int row0 = m_blk * BM + quad * 32;
       if (p.dbg == 2) { tc_fence_before(); mbar_arrive(tempty_bar(as)); continue; }
-      constexpr int kWb = (BN >= 128) ? 64 : 32;           // bf16 block width; fp32 output always uses 32-column blocks
+      constexpr int kWb = (BN >= 128) ? 64 : 32;           // block width of the generic (non-TMA) bf16 path
       if (p.tma_store) {
         const int r = quad * 32 + lane;                     // accumulator row == TMEM lane == staging row
-        const bool issuer = (e == half * 4) && lane == 0;
-        const uint32_t stg = stage_base + half * 16384;
+        const bool issuer = (e & 3) == 0 && lane == 0;
         const uint32_t tq = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
         if (p.out_f32) {
-          for (int j = half; j < BN / 32; j += 2) {
-            const int col0 = n_blk * BN + j * 32;
-            if (col0 >= p.N) break;                         // uniform across the half-group
-            epilogue_tma_block<float, 32>(p, &tm_c, tq + j * 32, stg, m_blk * BM, col0, r, half, issuer);
+          // fp32 rows of 32 columns are 128 bytes: two 16 KB staging tiles, groups 0 and 1 only
+          if (grp < 2) {
+            const uint32_t stg = stage_base + grp * 16384;
+            for (int j = grp; j < BN / 32; j += 2) {
+              const int col0 = n_blk * BN + j * 32;
+              if (col0 >= p.N) break;                       // uniform across the group
+              epilogue_tma_block<float, 32>(p, &tm_c, tq + j * 32, stg, m_blk * BM, col0, r, grp, issuer);
+            }
           }
         } else {
-          for (int j = half; j < BN / kWb; j += 2) {
-            const int col0 = n_blk * BN + j * kWb;
+          // bf16 rows of 32 columns are 64 bytes: four 8 KB staging tiles, one per group
+          const uint32_t stg = stage_base + grp * 8192;
+          for (int j = grp; j < BN / 32; j += 4) {
+            const int col0 = n_blk * BN + j * 32;
             if (col0 >= p.N) break;
-            epilogue_tma_block<bf16, kWb>(p, &tm_c, tq + j * kWb, stg, m_blk * BM, col0, r, half, issuer);
+            epilogue_tma_block<bf16, 32>(p, &tm_c, tq + j * 32, stg, m_blk * BM, col0, r, grp, issuer);
           }
         }
       } else if (p.out_f32) {
@@ -550,6 +580,24 @@ const CUtensorMap& get_map_c(const void* ptr, int64_t rows, int64_t cols, int64_
 }
 
 // Head-major cross-KV output [layers*B][G][L][D] bf16 (GemmArgs::hm_*): box = D x 128 positions of one (layer-image, group).
+// Activations of the head-major mode viewed as [B][L][K]: box = 64 k x 128 positions of one image (rows past L are zero-filled).
+const CUtensorMap& get_map_a3(const void* ptr, int64_t K, int L, int B, int64_t ld) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0)
+    throw std::runtime_error("gemm_tc: operand must be 16-byte aligned with a row stride that is a multiple of 8 elements");
+  MapKey key{ptr, L, K, ld, BM, BK, 2, 4, B, 0};
+  cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)L, (cuuint64_t)B};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)L * ld * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 1};
+  return cached_map(key, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+const CUtensorMap& get_map_hm3(const void* ptr, int D, int L, int64_t LBG, int box_cols) {
+  MapKey key{ptr, L, D, D, BM, box_cols, 2, 3, LBG, 0};
+  cuuint64_t gdim[3] = {(cuuint64_t)D, (cuuint64_t)L, (cuuint64_t)LBG};
+  cuuint64_t gstride[2] = {(cuuint64_t)D * 2, (cuuint64_t)L * D * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)BM, 1};
+  return cached_map(key, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, gdim, gstride, box,
+                    box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+}
 const CUtensorMap& get_map_hm(const void* ptr, int D, int L, int G, int64_t LB) {
   MapKey key{ptr, L, D, D, BM, D, 2, 2, G, LB};
   cuuint64_t gdim[4] = {(cuuint64_t)D, (cuuint64_t)L, (cuuint64_t)G, (cuuint64_t)LB};
@@ -568,25 +616,33 @@ void launch_cfg(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
     attr_set = true;
   }
   GemmArgs a = a_in;
-  const CUtensorMap& ma = get_map(a.A, a.M, a.K, a.lda, BM);
+  const CUtensorMap* ma_ptr = &get_map(a.A, a.M, a.K, a.lda, BM);
   const CUtensorMap& mb = get_map(a.W, a.N, a.K, a.ldw, BN);
   // TMA-store epilogue when the output is expressible as a tensor map; otherwise the generic register/shared path
   const int esz = a.out_f32 ? 4 : 2;
-  const int cw = a.out_f32 ? 32 : (BN >= 128 ? 64 : 32);
-  const CUtensorMap* mc = &ma;
+  const int cw = 32;                                  // columns per TMA-store box (bf16: 64-byte rows, fp32: 128-byte rows)
+  const CUtensorMap* mc = ma_ptr;
   a.tma_store = 0;
   static const bool no_tma_store = getenv("GSTVD_GEMM_NO_TMA_STORE") != nullptr;
+  static const bool no_tma_hm = getenv("GSTVD_GEMM_NO_TMA_HM") != nullptr;
   if (!no_tma_store && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0) {
     if (a.hm_D > 0) {
-      if (!a.out_f32 && cw == a.hm_D && a.hm_D == 64) { mc = &get_map_hm(a.C, a.hm_D, a.hm_L, a.hm_G, (int64_t)(a.N / (a.hm_D * a.hm_G)) * a.hm_B); a.tma_store = 1; }
+      if (!no_tma_hm && !a.out_f32 && a.hm_D % cw == 0 && a.M == a.hm_B * a.hm_L) {
+        const int64_t LB = (int64_t)(a.N / (a.hm_D * a.hm_G)) * a.hm_B;
+        mc = &get_map_hm3(a.C, a.hm_D, a.hm_L, LB * a.hm_G, cw);
+        a.hm_tpi = (a.hm_L + BM - 1) / BM;
+        ma_ptr = &get_map_a3(a.A, a.K, a.hm_L, a.hm_B, a.lda);
+        a.tma_store = 1;
+      }
     } else if ((a.ldc * esz) % 16 == 0) {
       mc = &get_map_c(a.C, a.M, a.N, a.ldc, esz, cw);
       a.tma_store = 1;
     }
   }
-  const int tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
+  const int tiles_m = a.hm_tpi > 0 ? a.hm_B * a.hm_tpi : (a.M + BM - 1) / BM;
+  const int tiles = tiles_m * ((a.N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_tc_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ma, mb, *mc, a);
+  gemm_tc_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(*ma_ptr, mb, *mc, a);
 }
 
 }  // namespace
