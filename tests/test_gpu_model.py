@@ -277,3 +277,46 @@ def test_full_bf16_vs_fp32(full_engines, full_cfgs, golden_dir):
     s32 = e32.generate(3, num_beams=5)
     print("beam-5 token agreement bf16 vs fp32:", (s16 == s32).float().mean().item())
     assert s16.shape == (3, 18)
+
+
+# ---- the ten-round loop of generate.py:122-233 ------------------------------------------------------
+def test_dialog_loop_matches_reference_loop(tiny_cfgs, tiny_sd):
+    """Questioner + teacher alternating rounds with history splices and the perplexity pass, fp32, greedy with 4-gram
+    blocking for questions: token ids, final history and abnormal flags identical; ppl within 1e-3 relative."""
+    from gst_visdial_b200 import synthetic as S, weights as W
+    from gst_visdial_b200.dialog import generate_dialogs
+    from oracle import dialog_loop as DL
+    enc_cfg, dec_cfg = tiny_cfgs
+    sd_q = W.synthetic_state_dict(enc_cfg, dec_cfg, seed=7)
+    a_model, _ = _build_model(W.TINY_ENC_CONFIG, W.TINY_DEC_CONFIG, tiny_sd, "fp32", model="enc_dec_a")
+    q_model, _ = _build_model(W.TINY_ENC_CONFIG, W.TINY_DEC_CONFIG, sd_q, "fp32", model="enc_dec_q")
+    batch = S.synthetic_batch(0, 3, vocab_size=enc_cfg.vocab_size, v_feature_size=enc_cfg.v_feature_size, cap_len=(150, 190))
+    kw_a = dict(temperature=1.0, top_k=1, top_p=0.0, ngram_blocking_size=0)
+    kw_q = dict(temperature=0.7, top_k=1, top_p=0.0, ngram_blocking_size=4)
+    rounds = 3                                     # long captions: the third round overflows 256 tokens for some rows
+    rq, ra, rp, rf, rids = DL.generate_dialogs(tiny_sd, enc_cfg, dec_cfg, batch, sd_q=sd_q, num_rounds=rounds, a_kwargs=kw_a, q_kwargs=kw_q)
+    res = generate_dialogs(a_model, batch, q_model=q_model, num_rounds=rounds, a_kwargs=kw_a, q_kwargs=kw_q, with_ppl=True)
+    assert torch.equal(res.questions.cpu(), rq), f"{res.questions.cpu()} vs {rq}"
+    assert torch.equal(res.answers.cpu(), ra)
+    assert torch.equal(res.enc_input_ids.cpu(), rids)
+    assert torch.equal(res.abnormal.cpu(), rf)
+    ok = torch.isfinite(rp)
+    assert torch.allclose(res.answer_ppl.cpu()[ok], rp[ok], rtol=1e-3)
+    assert rf.any(), "test should exercise the overflow path; lengthen the captions"
+
+
+def test_dialog_loop_beam_config2_shape(tiny_cfgs, tiny_sd):
+    """Config-2 shaped loop (teacher only, synthetic questions, beam 5, no ppl) against the oracle loop, fp32."""
+    from gst_visdial_b200 import synthetic as S, weights as W
+    from gst_visdial_b200.dialog import generate_dialogs
+    from oracle import dialog_loop as DL
+    enc_cfg, dec_cfg = tiny_cfgs
+    a_model, _ = _build_model(W.TINY_ENC_CONFIG, W.TINY_DEC_CONFIG, tiny_sd, "fp32")
+    B, rounds = 3, 3
+    batch = S.synthetic_batch(0, B, vocab_size=enc_cfg.vocab_size, v_feature_size=enc_cfg.v_feature_size)
+    ques = torch.stack([torch.stack([S.synthetic_utterance(i, r, enc_cfg.vocab_size) for r in range(rounds)]) for i in range(B)])
+    kw = dict(temperature=1.0, top_k=1, top_p=0.0, ngram_blocking_size=0, num_beams=5)
+    rq, ra, _, rf, rids = DL.generate_dialogs(tiny_sd, enc_cfg, dec_cfg, batch, questions=ques, num_rounds=rounds, a_kwargs=kw, with_ppl=False)
+    res = generate_dialogs(a_model, batch, questions=ques, num_rounds=rounds, a_kwargs=kw, with_ppl=False)
+    assert torch.equal(res.answers.cpu().masked_fill(res.answers.cpu() == 102, 0), ra)
+    assert torch.equal(res.enc_input_ids.cpu(), rids)
