@@ -573,7 +573,7 @@ void do_generate(gstvd_ctx* c, int B, const gstvd_gen_params& gp, const int64_t*
   }
   const DecodeGeom g = make_geom(c, B, K, T);
   // the sampling seed lives in device memory so that a captured graph can be replayed with a new seed
-  CUDA_CHECK(cudaMemcpyAsync(c->d_seed.p, &gp.seed, 8, cudaMemcpyHostToDevice, s));
+  c->launches += launch_set_u64((uint64_t*)c->d_seed.p, gp.seed, s);
   if (gp.mode == GSTVD_SELECT_BEAM) c->launches += launch_beam_init(beam_buffers(c), B, K, T, 101, s);
   else c->launches += launch_sample_init(B, T, 101, (int32_t*)c->seq.p, (int32_t*)c->cur_tokens.p, (int32_t*)c->prefix.p, T + 1, (int*)c->d_step.p, s);
 

@@ -133,6 +133,8 @@ int launch_sample_init(int rows, int T, int start_token, int32_t* seq, int32_t* 
                        int prefix_stride, int* d_step, cudaStream_t stream);
 int launch_sample_finalize(int rows, int T, int eos, const int32_t* seq, int64_t* out_ids, cudaStream_t stream);
 int launch_step_advance(int* d_step, cudaStream_t stream);
+// device-side scalar set (a pageable-memory cudaMemcpyAsync would synchronise the stream with the host)
+int launch_set_u64(uint64_t* dst, uint64_t v, cudaStream_t stream);
 
 // teacher-forced scoring helpers
 int launch_shift_labels(int B, int L, int64_t* dec_ids, int64_t* labels, int eos, cudaStream_t stream);

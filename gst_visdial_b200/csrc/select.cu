@@ -355,6 +355,8 @@ __global__ void sample_finalize_kernel(int rows, int T, int eos, const int32_t* 
   }
 }
 
+__global__ void set_u64_kernel(uint64_t* dst, uint64_t v) { if (threadIdx.x == 0 && blockIdx.x == 0) *dst = v; }
+
 __global__ void step_advance_kernel(int* d_step) { if (threadIdx.x == 0 && blockIdx.x == 0) *d_step += 1; }
 
 __global__ void shift_labels_kernel(int L, int64_t* __restrict__ ids, int64_t* __restrict__ labels, int eos) {
@@ -479,6 +481,10 @@ int launch_sample_init(int rows, int T, int start_token, int32_t* seq, int32_t* 
 }
 int launch_sample_finalize(int rows, int T, int eos, const int32_t* seq, int64_t* out_ids, cudaStream_t stream) {
   sample_finalize_kernel<<<(rows + 63) / 64, 64, 0, stream>>>(rows, T, eos, seq, out_ids);
+  return 1;
+}
+int launch_set_u64(uint64_t* dst, uint64_t v, cudaStream_t stream) {
+  set_u64_kernel<<<1, 32, 0, stream>>>(dst, v);
   return 1;
 }
 int launch_step_advance(int* d_step, cudaStream_t stream) {
