@@ -72,4 +72,10 @@ template <> struct Vec8<bf16> {
   }
 };
 
+// Programmatic dependent launch (PDL): a kernel launched with the attribute may start while its predecessor in the stream is
+// still running; pdl_wait() blocks until the predecessor has completed and its writes are visible, pdl_launch_dependents()
+// lets the successor start its own prologue.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace gstvd

@@ -25,6 +25,8 @@ template <typename T>
 __global__ void __launch_bounds__(128)
 dec_self_attn_kernel(DecodeGeom g, int layer, const T* __restrict__ qkv, T* __restrict__ cache, const int* __restrict__ d_step,
                      T* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x;
   const int h = blockIdx.y * 4 + warp;
@@ -114,73 +116,81 @@ template <> struct Raw16<float> {
   }
 };
 
+constexpr int kCrossThreads = 320;            // 10 warps: one thread per key in the score phase (Le = 293 in the real model)
+
 template <typename T, int KB, int D>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(kCrossThreads, 2)
 dec_cross_attn_kernel(DecodeGeom g, const T* __restrict__ q, const T* __restrict__ kv_layer, const float* __restrict__ enc_mask,
                       T* __restrict__ out) {
-  constexpr int EPL = 16 / sizeof(T);          // elements per 16-byte lane load
-  constexpr int LPR = D / EPL;                 // lanes per key row
-  constexpr int RPI = 32 / LPR;                // key rows per warp-wide load
-  constexpr int kWarps = 8;
-  constexpr int NIT = 10;                      // loads in flight per lane and operand: 8 warps x RPI x 10 keys per pass
+  constexpr int EPL = 16 / sizeof(T);          // elements per 16-byte load
+  constexpr int CPR = D / EPL;                 // 16-byte chunks per key row (8 for bf16, 16 for fp32)
+  constexpr int LPR = CPR;                     // phase 2: lanes per key row
+  constexpr int RPI = 32 / LPR;                // phase 2: key rows per warp-wide load
+  constexpr int kWarps = kCrossThreads / 32;
+  constexpr int NIT = 8;                       // phase 2: V loads in flight per lane (10 warps x RPI x 8 keys per pass)
   constexpr int kPass = kWarps * RPI * NIT;
   extern __shared__ float smem[];
   const int Le = g.Le;
   float* S = smem;                             // [KB][Le] scores, then probabilities
-  float* part = smem + KB * Le;                // [kWarps][KB][D] partial outputs
-  float* qs = part + kWarps * KB * D;          // [KB][D] queries (fp32)
+  float* part = smem + ((KB * Le + 3) & ~3);   // [kWarps][KB][D] partial outputs
+  float* qs = part + kWarps * KB * D;          // [KB][D] queries (fp32), 16-byte aligned
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, b = blockIdx.y;
-  const int sub = lane / LPR, chunk = lane % LPR;
   const T* Kp = kv_layer + ((int64_t)b * 2 * g.heads + h) * Le * D;
   const T* Vp = kv_layer + ((int64_t)b * 2 * g.heads + g.heads + h) * Le * D;
   const float* mrow = enc_mask ? enc_mask + (int64_t)b * Le : nullptr;
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
 
-  // K loads of the first pass are issued before anything else so that their latency overlaps the query staging
-  uint4 kreg[NIT];
+  // ---- phase 1: scores, one thread per key.  The whole key row (D elements) is loaded with CPR independent 16-byte
+  // loads issued back to back (in flight together), the queries are broadcast from shared memory; no shuffles. ----
+  const int j1 = threadIdx.x;
+  uint4 kreg[CPR];
+  float madd = 0.f;
+  if (j1 < Le) {
 #pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const int j = (it * kWarps + warp) * RPI + sub;
-    kreg[it] = (j < Le) ? *reinterpret_cast<const uint4*>(Kp + (int64_t)j * D + chunk * EPL) : zero4;
+    for (int c = 0; c < CPR; ++c) kreg[c] = *reinterpret_cast<const uint4*>(Kp + (int64_t)j1 * D + c * EPL);
+    madd = (1.0f - (mrow ? mrow[j1] : 1.f)) * -1e9f;
+  } else {
+#pragma unroll
+    for (int c = 0; c < CPR; ++c) kreg[c] = zero4;
   }
-  for (int i = threadIdx.x; i < g.K * D; i += blockDim.x) {
+  pdl_wait();                                 // the K rows above were written at prefill time; q comes from the previous kernel
+  for (int i = threadIdx.x; i < KB * D; i += blockDim.x) {
     const int k = i / D, d = i - k * D;
-    qs[k * D + d] = to_f32(q[((int64_t)(b * g.K + k)) * g.H + h * D + d]);
+    qs[i] = (k < g.K) ? to_f32(q[((int64_t)(b * g.K + k)) * g.H + h * D + d]) : 0.f;
   }
   __syncthreads();
   const float scale_div = sqrtf((float)D);
-  // ---- phase 1: scores ----
-  for (int base = 0; base < Le; base += kPass) {
-    if (base > 0) {
+  for (int j = j1; j < Le; j += blockDim.x) {
+    if (j != j1) {                             // only when Le > blockDim.x
 #pragma unroll
-      for (int it = 0; it < NIT; ++it) {
-        const int j = base + (it * kWarps + warp) * RPI + sub;
-        kreg[it] = (j < Le) ? *reinterpret_cast<const uint4*>(Kp + (int64_t)j * D + chunk * EPL) : zero4;
-      }
+      for (int c = 0; c < CPR; ++c) kreg[c] = *reinterpret_cast<const uint4*>(Kp + (int64_t)j * D + c * EPL);
+      madd = (1.0f - (mrow ? mrow[j] : 1.f)) * -1e9f;
     }
+    float dot[KB];
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      const int j = base + (it * kWarps + warp) * RPI + sub;
+    for (int k = 0; k < KB; ++k) dot[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPR; ++c) {
       float kr[EPL];
-      Raw16<T>::unpack(kreg[it], kr);
+      Raw16<T>::unpack(kreg[c], kr);
 #pragma unroll
       for (int k = 0; k < KB; ++k) {
-        float p = 0.f;
-        if (k < g.K) {
 #pragma unroll
-          for (int e = 0; e < EPL; ++e) p = fmaf(qs[k * D + chunk * EPL + e], kr[e], p);
-        }
-#pragma unroll
-        for (int o = LPR / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-        if (chunk == 0 && j < Le && k < g.K) {
-          const float m = mrow ? mrow[j] : 1.f;
-          S[k * Le + j] = p / scale_div + (1.0f - m) * -1e9f;
+        for (int e4 = 0; e4 < EPL; e4 += 4) {
+          const float4 qv = *reinterpret_cast<const float4*>(qs + k * D + c * EPL + e4);   // warp-wide broadcast
+          dot[k] = fmaf(qv.x, kr[e4], dot[k]); dot[k] = fmaf(qv.y, kr[e4 + 1], dot[k]);
+          dot[k] = fmaf(qv.z, kr[e4 + 2], dot[k]); dot[k] = fmaf(qv.w, kr[e4 + 3], dot[k]);
         }
       }
     }
+#pragma unroll
+    for (int k = 0; k < KB; ++k)
+      if (k < g.K) S[k * Le + j] = dot[k] / scale_div + madd;
   }
   // V loads of the first pass: in flight while the softmax runs
+  const int sub = lane / LPR, chunk = lane % LPR;
   uint4 vreg[NIT];
 #pragma unroll
   for (int it = 0; it < NIT; ++it) {
@@ -199,7 +209,7 @@ dec_cross_attn_kernel(DecodeGeom g, const T* __restrict__ q, const T* __restrict
     for (int j = lane; j < Le; j += 32) S[k * Le + j] = S[k * Le + j] / sum;
   }
   __syncthreads();
-  // ---- phase 2: P * V ----
+  // ---- phase 2: P * V (lanes split the head dimension; every V byte is read once, coalesced) ----
   float acc[KB][EPL];
 #pragma unroll
   for (int k = 0; k < KB; ++k)
@@ -256,9 +266,10 @@ dec_cross_attn_kernel(DecodeGeom g, const T* __restrict__ q, const T* __restrict
 
 template <typename T, int KB>
 void launch_cross_kb(const DecodeGeom& g, const T* q, const T* kv_layer, const float* enc_mask, T* out, cudaStream_t stream) {
-  const size_t smem = ((size_t)KB * g.Le + (size_t)8 * KB * 64 + (size_t)KB * 64) * sizeof(float);
+  const size_t s_elems = ((size_t)KB * g.Le + 3) & ~size_t(3);          // keeps the query tile 16-byte aligned
+  const size_t smem = (s_elems + (size_t)(kCrossThreads / 32) * KB * 64 + (size_t)KB * 64) * sizeof(float);
   dim3 grid(g.heads, g.B);
-  dec_cross_attn_kernel<T, KB, 64><<<grid, 256, smem, stream>>>(g, q, kv_layer, enc_mask, out);
+  launch_k(dec_cross_attn_kernel<T, KB, 64>, grid, dim3(kCrossThreads), smem, stream, g, q, kv_layer, enc_mask, out);
 }
 template <typename T>
 void launch_cross_t(const DecodeGeom& g, const void* q, const void* kv_layer, const float* enc_mask, void* out, cudaStream_t stream) {
@@ -276,6 +287,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 reorder_cache_kernel(DecodeGeom g, T* __restrict__ cache, const int32_t* __restrict__ beam_idx, const int* __restrict__ d_len,
                      int len_host, const uint8_t* __restrict__ d_skip) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.x, lk = blockIdx.y;
   if (d_skip && d_skip[b]) return;
   const int len = d_len ? (*d_len + 1) : len_host;
@@ -309,8 +322,8 @@ int launch_dec_self_attn(int dtype, const DecodeGeom& g, int layer, const void* 
   if (g.D != 64 && g.D != 128) throw std::runtime_error("dec_self_attn: head_dim must be 64 or 128");
   if (g.T > kMaxSteps) throw std::runtime_error("dec_self_attn: at most 32 cached positions");
   dim3 grid(g.B * g.K, (g.heads + 3) / 4);
-  if (dtype == kF32) dec_self_attn_kernel<float><<<grid, 128, 0, stream>>>(g, layer, (const float*)qkv, (float*)self_cache, d_step, (float*)out);
-  else dec_self_attn_kernel<bf16><<<grid, 128, 0, stream>>>(g, layer, (const bf16*)qkv, (bf16*)self_cache, d_step, (bf16*)out);
+  if (dtype == kF32) launch_k(dec_self_attn_kernel<float>, grid, dim3(128), 0, stream, g, layer, (const float*)qkv, (float*)self_cache, d_step, (float*)out);
+  else launch_k(dec_self_attn_kernel<bf16>, grid, dim3(128), 0, stream, g, layer, (const bf16*)qkv, (bf16*)self_cache, d_step, (bf16*)out);
   return 1;
 }
 
@@ -339,8 +352,8 @@ int launch_reorder_cache(int dtype, const DecodeGeom& g, void* self_cache, const
   if (g.K > kMaxBeams) throw std::runtime_error("reorder_cache: at most 8 beams");
   if (g.H % 8) throw std::runtime_error("reorder_cache: hidden % 8 != 0");
   dim3 grid(g.B, g.layers * 2);
-  if (dtype == kF32) reorder_cache_kernel<float><<<grid, 256, 0, stream>>>(g, (float*)self_cache, beam_idx, d_len, len_host, d_skip);
-  else reorder_cache_kernel<bf16><<<grid, 256, 0, stream>>>(g, (bf16*)self_cache, beam_idx, d_len, len_host, d_skip);
+  if (dtype == kF32) launch_k(reorder_cache_kernel<float>, grid, dim3(256), 0, stream, g, (float*)self_cache, beam_idx, d_len, len_host, d_skip);
+  else launch_k(reorder_cache_kernel<bf16>, grid, dim3(256), 0, stream, g, (bf16*)self_cache, beam_idx, d_len, len_host, d_skip);
   return 1;
 }
 

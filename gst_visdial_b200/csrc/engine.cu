@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <stdexcept>
@@ -22,6 +23,11 @@
 #include "kernels.h"
 
 using namespace gstvd;
+
+namespace gstvd {
+bool& pdl_flag() { static thread_local bool f = false; return f; }
+bool carveout_max_flag() { static const bool on = getenv("GSTVD_CARVEOUT_MAX") != nullptr; return on; }
+}  // namespace gstvd
 
 namespace {
 
@@ -508,6 +514,8 @@ BeamBuffers beam_buffers(gstvd_ctx* c) {
 void decode_step(gstvd_ctx* c, const DecodeGeom& g, const gstvd_gen_params& gp, const int64_t* hist_ids, const int64_t* hist_seg,
                  int Lh, cudaStream_t s) {
   Exec X{c, s};
+  struct PdlScope { bool prev; explicit PdlScope(bool on) : prev(pdl_flag()) { pdl_flag() = on; } ~PdlScope() { pdl_flag() = prev; } };
+  PdlScope pdl_scope(!(c->cfg.flags & GSTVD_FLAG_NO_PDL));
   const int H = c->H, M = g.B * g.K;
   const int* d_step = (const int*)c->d_step.p;
   c->launches += launch_embed_step(c->dtype, M, H, (const int32_t*)c->cur_tokens.p, d_step, c->word, c->pos, c->type,
@@ -919,6 +927,9 @@ int gstvd_op_linear(gstvd_ctx* c, int dtype, int M, int N, int K, const float* a
       void* c16 = nullptr;
       if (bf16_out) { c16 = sc.get((size_t)M * N * 2); g.C = c16; g.out_f32 = 0; }
       gemm_tc_init();
+      static const bool want_times = getenv("GSTVD_GEMM_TIMES") != nullptr;   // measurement aid: per-CTA phase timestamps
+      unsigned long long* d_times = nullptr;
+      if (want_times) { d_times = (unsigned long long*)sc.get(256 * 8 * 8); CUDA_CHECK(cudaMemsetAsync(d_times, 0, 256 * 8 * 8, s)); g.dbg_times = d_times; }
       if (c->cfg.flags & GSTVD_FLAG_DEBUG_SIMT_GEMM) c->launches += launch_gemm_simt(g, kBF16, s);
       else {
         const bool prof = c->profiling && c->prof_used < c->prof_pool.size();
@@ -933,6 +944,16 @@ int gstvd_op_linear(gstvd_ctx* c, int dtype, int M, int N, int K, const float* a
       }
       if (c16) c->launches += launch_cast_to_f32(kBF16, c16, out, (int64_t)M * N, s);
       CUDA_CHECK(cudaStreamSynchronize(s));
+      if (d_times) {
+        std::vector<unsigned long long> h(256 * 8);
+        CUDA_CHECK(cudaMemcpy(h.data(), d_times, h.size() * 8, cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull; int ctas = 0;
+        for (int i = 0; i < 256; ++i) if (h[i * 8]) { t0 = std::min(t0, h[i * 8]); ++ctas; }
+        double sum[8] = {0}, mx[8] = {0};
+        for (int i = 0; i < 256; ++i) if (h[i * 8]) for (int j = 0; j < 8; ++j) { double v = h[i * 8 + j] ? (double)(h[i * 8 + j] - t0) : 0; sum[j] += v; mx[j] = std::max(mx[j], v); }
+        fprintf(stderr, "[gemm times M=%d N=%d K=%d ctas=%d] mean/max ns since first CTA start: start %.0f/%.0f prologue %.0f/%.0f pdl_wait %.0f/%.0f first_full %.0f/%.0f last_commit %.0f/%.0f epi_begin %.0f/%.0f epi_end %.0f/%.0f end %.0f/%.0f\n",
+                M, N, K, ctas, sum[0] / ctas, mx[0], sum[1] / ctas, mx[1], sum[2] / ctas, mx[2], sum[3] / ctas, mx[3], sum[4] / ctas, mx[4], sum[5] / ctas, mx[5], sum[6] / ctas, mx[6], sum[7] / ctas, mx[7]);
+      }
     }
   });
 }

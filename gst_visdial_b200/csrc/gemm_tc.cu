@@ -389,6 +389,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned long long* stamps = p.dbg_times ? p.dbg_times + (size_t)blockIdx.x * 8 : nullptr;
+  if (stamps && threadIdx.x == 0) stamps[0] = global_ns();
   const int tiles_n = (p.N + BN - 1) / BN;
   const int tiles_m = p.hm_tpi > 0 ? p.hm_B * p.hm_tpi : (p.M + BM - 1) / BM;
   const int num_tiles = tiles_m * tiles_n;
@@ -407,22 +409,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (stamps && threadIdx.x == 0) stamps[1] = global_ns();
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
     if (lane == 0) {
+      pdl_launch_dependents();                       // the next kernel may start its prologue / weight prefetch
       int stage = 0; uint32_t phase = 0;
+      bool first = true;
+      auto load_a = [&](int st, int kb, int m_blk) {
+        if (p.hm_tpi > 0) {
+          const int img = m_blk / p.hm_tpi;
+          tma_load_3d(a_base + st * Cfg::kABytes, &tm_a, kb * BK, (m_blk - img * p.hm_tpi) * BM, img, full_bar(st));
+        } else {
+          tma_load_2d(a_base + st * Cfg::kABytes, &tm_a, kb * BK, m_blk * BM, full_bar(st));
+        }
+      };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        int kb0 = 0;
+        if (first) {
+          // Programmatic dependent launch: the weights (B) never depend on the previous kernel, so the first ring of
+          // B tiles is requested before waiting for it; the activations (A) are requested after the wait.
+          first = false;
+          const int pre = num_kb < kStages ? num_kb : kStages;
+          for (int st = 0; st < pre; ++st) {
+            mbar_arrive_expect_tx(full_bar(st), Cfg::kABytes + Cfg::kBBytes);
+            tma_load_2d(b_base + st * Cfg::kBBytes, &tm_b, st * BK, n_blk * BN, full_bar(st));
+          }
+          pdl_wait();
+          if (stamps) stamps[2] = global_ns();
+          for (int st = 0; st < pre; ++st) load_a(st, st, m_blk);
+          kb0 = pre;
+          if (pre == kStages) { stage = 0; phase = 1u; } else { stage = pre; }
+        }
+        for (int kb = kb0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), Cfg::kABytes + Cfg::kBBytes);
-          if (p.hm_tpi > 0) {
-            const int img = m_blk / p.hm_tpi;
-            tma_load_3d(a_base + stage * Cfg::kABytes, &tm_a, kb * BK, (m_blk - img * p.hm_tpi) * BM, img, full_bar(stage));
-          } else {
-            tma_load_2d(a_base + stage * Cfg::kABytes, &tm_a, kb * BK, m_blk * BM, full_bar(stage));
-          }
+          load_a(stage, kb, m_blk);
           tma_load_2d(b_base + stage * Cfg::kBBytes, &tm_b, kb * BK, n_blk * BN, full_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -441,6 +465,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);         // TMA bytes have landed
           tc_fence_after();
+          if (stamps && iter == 0 && kb == 0) stamps[3] = global_ns();
           const uint64_t a_desc = make_smem_desc(a_base + stage * Cfg::kABytes);
           const uint64_t b_desc = make_smem_desc(b_base + stage * Cfg::kBBytes);
 #pragma unroll
@@ -449,7 +474,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             if (p.dbg != 3) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));             // frees the smem slot when these MMAs retire
-          if (kb == num_kb - 1) umma_commit(tfull_bar(as));
+          if (kb == num_kb - 1) { umma_commit(tfull_bar(as)); if (stamps) stamps[4] = global_ns(); }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -470,6 +495,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
+      if (stamps && e == 0 && lane == 0) stamps[5] = global_ns();
       const int row0 = m_blk * BM + quad * 32;
       if (p.dbg == 2) { tc_fence_before(); mbar_arrive(tempty_bar(as)); continue; }
       constexpr int kWb = (BN >= 128) ? 64 : 32;           // block width of the generic (non-TMA) bf16 path
@@ -512,11 +538,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       tc_fence_before();
       mbar_arrive(tempty_bar(as));
     }
-    if (p.tma_store && (e & 3) == 0 && lane == 0) bulk_wait0();   // outstanding TMA stores must finish before smem goes away
+    // the staging tiles must have been read before the CTA's shared memory goes away; the global writes themselves are
+    // complete (and visible to the next kernel) at grid end like any other store
+    if (p.tma_store && (e & 3) == 0 && lane == 0) bulk_wait_read0();
+    if (stamps && e == 0 && lane == 0) stamps[6] = global_ns();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  if (stamps && threadIdx.x == 32) stamps[7] = global_ns();
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -642,7 +672,7 @@ void launch_cfg(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
   const int tiles_m = a.hm_tpi > 0 ? a.hm_B * a.hm_tpi : (a.M + BM - 1) / BM;
   const int tiles = tiles_m * ((a.N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_tc_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(*ma_ptr, mb, *mc, a);
+  launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, stream, *ma_ptr, mb, *mc, a);
 }
 
 }  // namespace

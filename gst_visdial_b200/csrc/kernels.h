@@ -4,7 +4,33 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 namespace gstvd {
+
+// Set by the engine around the decode step: launch with the programmatic-stream-serialization attribute (PDL).
+bool& pdl_flag();
+bool carveout_max_flag();   // env GSTVD_CARVEOUT_MAX=1: pin the shared-memory carve-out of every launch_k kernel (measured: no gain)
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_flag() ? 1 : 0;
+  // Optional experiment: identical L1/shared-memory carve-out for every kernel of the decode chain (measured: no effect).
+  static thread_local const void* configured[64];
+  static thread_local int n_configured = 0;
+  bool seen = false;
+  for (int i = 0; i < n_configured; ++i) seen |= (configured[i] == (const void*)kernel);
+  if (!seen && n_configured < 64) {
+    if (carveout_max_flag()) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured[n_configured++] = (const void*)kernel;
+  }
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
 enum DType { kF32 = 0, kBF16 = 1 };
 
@@ -22,6 +48,7 @@ struct GemmArgs {
   int hm_D = 0, hm_L = 0, hm_G = 0, hm_B = 0;
   int hm_tpi = 0;      // set by launch_gemm_tc: head-major TMA mode, M tiles per image (tiles never straddle images)
   int tma_store = 0;   // set by launch_gemm_tc: epilogue stores through a TMA tensor map
+  unsigned long long* dbg_times = nullptr;   // measurement aid: per-CTA globaltimer stamps (8 per CTA)
   int dbg = 0;   // measurement aid (env GSTVD_GEMM_DBG): 1 = epilogue without global stores, 2 = epilogue skipped, 3 = no MMA
 };
 

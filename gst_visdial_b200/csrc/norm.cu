@@ -56,6 +56,8 @@ template <typename T>
 __global__ void __launch_bounds__(kRowsPerBlock * 32)
 add_layernorm_kernel(int rows, int width, const T* __restrict__ x, int64_t ldx, const T* __restrict__ res, int64_t ldr,
                      const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ y, int64_t ldy) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -112,6 +114,8 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32)
 embed_step_kernel(int rows, int width, const int32_t* __restrict__ tokens, const int* __restrict__ d_step,
                   const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type,
                   const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ y) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -240,9 +244,9 @@ int launch_add_layernorm(int dtype, int rows, int width, const void* x, int64_t 
   if (rows <= 0) return 0;
   check_width(width);
   if (dtype == kF32)
-    add_layernorm_kernel<float><<<grid_rows(rows), kRowsPerBlock * 32, 0, stream>>>(rows, width, (const float*)x, ldx, (const float*)residual, ldr, gamma, beta, (float*)y, ldy);
+    launch_k(add_layernorm_kernel<float>, grid_rows(rows), kRowsPerBlock * 32, 0, stream, rows, width, (const float*)x, ldx, (const float*)residual, ldr, gamma, beta, (float*)y, ldy);
   else
-    add_layernorm_kernel<bf16><<<grid_rows(rows), kRowsPerBlock * 32, 0, stream>>>(rows, width, (const bf16*)x, ldx, (const bf16*)residual, ldr, gamma, beta, (bf16*)y, ldy);
+    launch_k(add_layernorm_kernel<bf16>, grid_rows(rows), kRowsPerBlock * 32, 0, stream, rows, width, (const bf16*)x, ldx, (const bf16*)residual, ldr, gamma, beta, (bf16*)y, ldy);
   return 1;
 }
 
@@ -263,9 +267,9 @@ int launch_embed_step(int dtype, int rows, int width, const int32_t* tokens, con
   if (rows <= 0) return 0;
   check_width(width);
   if (dtype == kF32)
-    embed_step_kernel<float><<<grid_rows(rows), kRowsPerBlock * 32, 0, stream>>>(rows, width, tokens, d_step, word, pos, type, gamma, beta, (float*)y);
+    launch_k(embed_step_kernel<float>, grid_rows(rows), kRowsPerBlock * 32, 0, stream, rows, width, tokens, d_step, word, pos, type, gamma, beta, (float*)y);
   else
-    embed_step_kernel<bf16><<<grid_rows(rows), kRowsPerBlock * 32, 0, stream>>>(rows, width, tokens, d_step, word, pos, type, gamma, beta, (bf16*)y);
+    launch_k(embed_step_kernel<bf16>, grid_rows(rows), kRowsPerBlock * 32, 0, stream, rows, width, tokens, d_step, word, pos, type, gamma, beta, (bf16*)y);
   return 1;
 }
 

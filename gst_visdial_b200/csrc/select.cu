@@ -33,6 +33,8 @@ row_select_kernel(int V, const float* __restrict__ logits, int64_t ldl, int mode
   __shared__ double s_d[32];
   __shared__ int s_i[32];
   __shared__ int s_bcast_i;
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* __restrict__ x = logits + (int64_t)row * ldl;
   float v[kSlots];
@@ -180,6 +182,8 @@ __device__ void hyp_add(const BeamBuffers& bb, int b, int K, int T, const int32_
 __global__ void beam_step_kernel(BeamBuffers bb, int B, int K, int T, int V, int nsel, const float* __restrict__ sel_val,
                                  const int32_t* __restrict__ sel_idx, int eos, int32_t* out_beam_idx, int32_t* out_tokens,
                                  float* out_scores) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int t = *bb.d_step;
@@ -256,6 +260,8 @@ ngram_ban_kernel(int Lh, const int64_t* __restrict__ hist_ids, const int64_t* __
                  const int32_t* __restrict__ prefix, int prefix_stride, const int* __restrict__ d_step, int n,
                  int32_t* __restrict__ ban_tokens, int32_t* __restrict__ ban_count, int ban_stride) {
   __shared__ int cnt;
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x;
   if (threadIdx.x == 0) cnt = 0;
   __syncthreads();
@@ -304,6 +310,8 @@ __global__ void sample_init_kernel(int rows, int T, int start_token, int32_t* se
 __global__ void sample_step_kernel(int rows, int T, int nsel, const float* __restrict__ sel_val, const int32_t* __restrict__ sel_idx,
                                    int top_k, float top_p, uint64_t seed, const uint64_t* __restrict__ d_seed,
                                    const int* __restrict__ d_step, int eos, int32_t* seq, int32_t* cur_tokens, int32_t* prefix, int prefix_stride, int32_t* out_tokens) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   const int step = *d_step;
@@ -357,7 +365,10 @@ __global__ void sample_finalize_kernel(int rows, int T, int eos, const int32_t* 
 
 __global__ void set_u64_kernel(uint64_t* dst, uint64_t v) { if (threadIdx.x == 0 && blockIdx.x == 0) *dst = v; }
 
-__global__ void step_advance_kernel(int* d_step) { if (threadIdx.x == 0 && blockIdx.x == 0) *d_step += 1; }
+__global__ void step_advance_kernel(int* d_step) {
+  pdl_wait();
+  if (threadIdx.x == 0 && blockIdx.x == 0) *d_step += 1;
+}
 
 __global__ void shift_labels_kernel(int L, int64_t* __restrict__ ids, int64_t* __restrict__ labels, int eos) {
   const int b = blockIdx.x;
@@ -437,7 +448,7 @@ int launch_row_select(int rows, int V, const float* logits, int64_t ldl, int mod
   if (rows <= 0) return 0;
   if (V > kSelThreads * kSlots) throw std::runtime_error("row_select: vocab > 32768");
   if (nsel > kSelMax || nsel < 1) throw std::runtime_error("row_select: nsel out of range");
-  row_select_kernel<<<rows, kSelThreads, 0, stream>>>(V, logits, ldl, mode, row_bias, temperature, ban_tokens, ban_count,
+  launch_k(row_select_kernel, dim3(rows), dim3(kSelThreads), 0, stream, V, logits, ldl, mode, row_bias, temperature, ban_tokens, ban_count,
                                                       ban_stride, nsel, sel_val, sel_idx, logz);
   return 1;
 }
@@ -451,7 +462,7 @@ int launch_beam_step(const BeamBuffers& bb, int B, int K, int T, int V, int nsel
                      const int32_t* sel_idx, int eos, int32_t* out_beam_idx, int32_t* out_tokens, float* out_scores,
                      cudaStream_t stream) {
   if (K > 8 || T > kHypMaxT) throw std::runtime_error("beam_step: K <= 8 and T <= 32");
-  beam_step_kernel<<<(B + 31) / 32, 32, 0, stream>>>(bb, B, K, T, V, nsel, sel_val, sel_idx, eos, out_beam_idx, out_tokens, out_scores);
+  launch_k(beam_step_kernel, dim3((B + 31) / 32), dim3(32), 0, stream, bb, B, K, T, V, nsel, sel_val, sel_idx, eos, out_beam_idx, out_tokens, out_scores);
   return 1;
 }
 int launch_beam_finalize(const BeamBuffers& bb, int B, int K, int T, int eos, int64_t* out_ids, float* out_scores,
@@ -463,14 +474,14 @@ int launch_ngram_ban(int rows, int Lh, const int64_t* hist_ids, const int64_t* h
                      int prefix_stride, const int* d_step, int n, int32_t* ban_tokens, int32_t* ban_count, int ban_stride,
                      cudaStream_t stream) {
   if (rows <= 0) return 0;
-  ngram_ban_kernel<<<rows, 256, 0, stream>>>(Lh, hist_ids, hist_seg, prefix, prefix_stride, d_step, n, ban_tokens, ban_count, ban_stride);
+  launch_k(ngram_ban_kernel, dim3(rows), dim3(256), 0, stream, Lh, hist_ids, hist_seg, prefix, prefix_stride, d_step, n, ban_tokens, ban_count, ban_stride);
   return 1;
 }
 int launch_sample_step(int rows, int T, int nsel, const float* sel_val, const int32_t* sel_idx, int top_k, float top_p,
                        uint64_t seed, const uint64_t* d_seed, const int* d_step, int eos, int32_t* seq, int32_t* cur_tokens, int32_t* prefix,
                        int prefix_stride, int32_t* out_tokens, cudaStream_t stream) {
   if (top_k < 1 || top_k > nsel) throw std::runtime_error("sample_step: top_k out of range");
-  sample_step_kernel<<<(rows + 63) / 64, 64, 0, stream>>>(rows, T, nsel, sel_val, sel_idx, top_k, top_p, seed, d_seed, d_step, eos, seq,
+  launch_k(sample_step_kernel, dim3((rows + 63) / 64), dim3(64), 0, stream, rows, T, nsel, sel_val, sel_idx, top_k, top_p, seed, d_seed, d_step, eos, seq,
                                                           cur_tokens, prefix, prefix_stride, out_tokens);
   return 1;
 }
@@ -488,7 +499,7 @@ int launch_set_u64(uint64_t* dst, uint64_t v, cudaStream_t stream) {
   return 1;
 }
 int launch_step_advance(int* d_step, cudaStream_t stream) {
-  step_advance_kernel<<<1, 32, 0, stream>>>(d_step);
+  launch_k(step_advance_kernel, dim3(1), dim3(32), 0, stream, d_step);
   return 1;
 }
 int launch_shift_labels(int B, int L, int64_t* dec_ids, int64_t* labels, int eos, cudaStream_t stream) {

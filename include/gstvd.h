@@ -76,6 +76,7 @@ typedef struct {
 
 #define GSTVD_FLAG_NO_CUDA_GRAPH 1   /* launch decode steps eagerly instead of replaying a captured graph */
 #define GSTVD_FLAG_DEBUG_SIMT_GEMM 2 /* debugging aid: route bf16 GEMMs through the SIMT kernel */
+#define GSTVD_FLAG_NO_PDL 8          /* decode-step kernels without programmatic dependent launch */
 #define GSTVD_FLAG_GENERIC_ATTENTION 4 /* debugging aid: route bf16 attention through the generic SIMT kernel */
 
 typedef struct {
