@@ -3,6 +3,8 @@
 Tolerances (BASELINE.json north_star): fp32 logits <= 1e-3 max abs, greedy / beam ids identical in fp32;
 bf16: 2e-2 relative, defined here as rms(delta) / rms(reference) over the logits of valid positions.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -320,3 +322,19 @@ def test_dialog_loop_beam_config2_shape(tiny_cfgs, tiny_sd):
     res = generate_dialogs(a_model, batch, questions=ques, num_rounds=rounds, a_kwargs=kw, with_ppl=False)
     assert torch.equal(res.answers.cpu().masked_fill(res.answers.cpu() == 102, 0), ra)
     assert torch.equal(res.enc_input_ids.cpu(), rids)
+
+
+def test_generate_cli_synthetic(tmp_path):
+    """generate.py end to end (questioner + teacher, sampling with 4-gram blocking, ppl) on the tiny configs."""
+    import json
+    import subprocess
+    import sys
+    from gst_visdial_b200 import weights as W
+    from helpers import ROOT
+    cmd = [sys.executable, os.path.join(ROOT, "generate.py"), "-synthetic", "5", "-batch_size", "4", "-num_rounds", "2",
+           "-model_enc_config", W.TINY_ENC_CONFIG, "-model_dec_config", W.TINY_DEC_CONFIG, "-save_path", str(tmp_path), "-save_name", "o.json",
+           "-compute_dtype", "bf16"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = json.load(open(tmp_path / "o.json"))
+    assert len(out) == 5 and len(out[0]["dialog"]) == 2 and out[0]["dialog"][0]["answer_ppl"] > 0
