@@ -21,10 +21,30 @@ namespace {
 constexpr int kMaxSteps = 32;     // one score per lane
 constexpr int kMaxBeams = 8;
 
+template <typename T> struct Raw16 {};
+template <> struct Raw16<bf16> {
+  static __device__ __forceinline__ void unpack(const uint4& r, float (&o)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+  }
+};
+template <> struct Raw16<float> {
+  static __device__ __forceinline__ void unpack(const uint4& r, float (&o)[4]) {
+    o[0] = __uint_as_float(r.x); o[1] = __uint_as_float(r.y); o[2] = __uint_as_float(r.z); o[3] = __uint_as_float(r.w);
+  }
+};
+
+// Self-attention of one new position per (beam row, head) over the persistent cache (one warp per (row, head)).
+// Scores: lane t owns cached position t and reads its whole key row (16-byte loads, all issued back to back) against the
+// query held in shared memory - no serial chain of load + warp-reduction per position; the new position's score is one
+// warp reduction.  P*V: lanes split the head dimension, the value rows of 6 positions are in flight at a time.
 template <typename T>
 __global__ void __launch_bounds__(128)
 dec_self_attn_kernel(DecodeGeom g, int layer, const T* __restrict__ qkv, T* __restrict__ cache, const int* __restrict__ d_step,
                      T* __restrict__ out) {
+  constexpr int EPL = 16 / sizeof(T);
+  __shared__ __align__(16) float qs[4][128];
   pdl_wait();
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -42,6 +62,7 @@ dec_self_attn_kernel(DecodeGeom g, int layer, const T* __restrict__ qkv, T* __re
     if (u < nd) {
       const int d = lane + 32 * u;
       q[u] = to_f32(qrow[d]); kn[u] = to_f32(qrow[H + d]); vn[u] = to_f32(qrow[2 * H + d]);
+      qs[warp][d] = q[u];
     } else { q[u] = kn[u] = vn[u] = 0.f; }
   }
   // cache row of (kv, position t) for this beam/head
@@ -54,67 +75,67 @@ dec_self_attn_kernel(DecodeGeom g, int layer, const T* __restrict__ qkv, T* __re
     for (int u = 0; u < 4; ++u)
       if (u < nd) { kc[lane + 32 * u] = from_f32<T>(kn[u]); vc[lane + 32 * u] = from_f32<T>(vn[u]); }
   }
-  // In bf16 mode the reference-equivalent value of the new key/value is the ROUNDED one (it is what later steps read)
-#pragma unroll
-  for (int u = 0; u < 4; ++u) { kn[u] = to_f32(from_f32<T>(kn[u])); vn[u] = to_f32(from_f32<T>(vn[u])); }
-
+  __syncwarp();
   const float scale_div = sqrtf((float)D);
+  // score of the new position: one reduction over the lanes' dims
+  float part = 0.f;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) part = fmaf(q[u], kn[u], part);
+  const float s_new = warp_sum(part) / scale_div;
+  // scores of the cached positions: lane t reads key row t
   float my_score = -INFINITY;
-  for (int t = 0; t <= step; ++t) {
-    float part = 0.f;
-    if (t == step) {
+  if (lane < step) {
+    const T* kc = cache_ptr(0, lane);
+    float dot = 0.f;
+    for (int c = 0; c < D / EPL; ++c) {
+      float kr[EPL];
+      const uint4 raw = *reinterpret_cast<const uint4*>(kc + c * EPL);
+      Raw16<T>::unpack(raw, kr);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) part = fmaf(q[u], kn[u], part);
-    } else {
-      const T* kc = cache_ptr(0, t);
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (u < nd) part = fmaf(q[u], to_f32(kc[lane + 32 * u]), part);
+      for (int e4 = 0; e4 < EPL; e4 += 4) {
+        const float4 qv = *reinterpret_cast<const float4*>(&qs[warp][c * EPL + e4]);
+        dot = fmaf(qv.x, kr[e4], dot); dot = fmaf(qv.y, kr[e4 + 1], dot);
+        dot = fmaf(qv.z, kr[e4 + 2], dot); dot = fmaf(qv.w, kr[e4 + 3], dot);
+      }
     }
-    const float s = warp_sum(part) / scale_div;
-    if (lane == t) my_score = s;
+    my_score = dot / scale_div;
+  } else if (lane == step) {
+    my_score = s_new;
   }
   const float mx = warp_max(my_score);
   const float e = (lane <= step) ? expf(my_score - mx) : 0.f;
   const float sum = warp_sum(e);
   const float pr = e / sum;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int t = 0; t <= step; ++t) {
-    const float pt = __shfl_sync(0xffffffffu, pr, t);
-    if (t == step) {
+  for (int t0 = 0; t0 < step; t0 += 6) {
+    float vv[6][4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) acc[u] = fmaf(pt, vn[u], acc[u]);
-    } else {
-      const T* vc = cache_ptr(1, t);
+    for (int i = 0; i < 6; ++i) {
+      const int t = t0 + i;
+      const T* vc = cache_ptr(1, t < step ? t : 0);
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (u < nd) acc[u] = fmaf(pt, to_f32(vc[lane + 32 * u]), acc[u]);
+      for (int u = 0; u < 4; ++u) vv[i][u] = (u < nd && t < step) ? to_f32(vc[lane + 32 * u]) : 0.f;
     }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const float pt = __shfl_sync(0xffffffffu, pr, (t0 + i) & 31);
+      if (t0 + i < step) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = fmaf(pt, vv[i][u], acc[u]);
+      }
+    }
+  }
+  {
+    const float pt = __shfl_sync(0xffffffffu, pr, step);
+    // in bf16 mode later steps read the ROUNDED new value from the cache; use the same value now
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = fmaf(pt, to_f32(from_f32<T>(vn[u])), acc[u]);
   }
   T* o = out + (int64_t)row * H + h * D;
 #pragma unroll
   for (int u = 0; u < 4; ++u)
     if (u < nd) o[lane + 32 * u] = from_f32<T>(acc[u]);
 }
-
-// Cross-attention of all K beam rows of one image over that image's K/V for one head (HBM-bound streaming kernel).
-// grid (heads, images); every K/V byte is read from global exactly once per CTA, by one warp, with fully coalesced
-// 16-byte loads (a head's [Le][D] block is contiguous in the head-major cache), and is reused for all K beams from
-// registers.  Exact (two-pass) softmax: scores -> shared memory -> per-beam softmax -> P*V, so the arithmetic is the
-// reference's softmax(QK^T/sqrt(d) + (1-m)*-1e9) V, not an online rescaling.
-template <typename T> struct Raw16 {};
-template <> struct Raw16<bf16> {
-  static __device__ __forceinline__ void unpack(const uint4& r, float (&o)[8]) {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
-  }
-};
-template <> struct Raw16<float> {
-  static __device__ __forceinline__ void unpack(const uint4& r, float (&o)[4]) {
-    o[0] = __uint_as_float(r.x); o[1] = __uint_as_float(r.y); o[2] = __uint_as_float(r.z); o[3] = __uint_as_float(r.w);
-  }
-};
 
 constexpr int kCrossThreads = 320;            // 10 warps: one thread per key in the score phase (Le = 293 in the real model)
 

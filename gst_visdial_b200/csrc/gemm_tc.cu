@@ -493,6 +493,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
       const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
       const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
+      if (p.bias != nullptr && lane == 0) {              // pull this tile's bias segment into L1 while the main loop runs
+        const int c0 = n_blk * BN + (e & 7) * (BN / 8);
+        if (c0 < p.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + c0));
+      }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       if (stamps && e == 0 && lane == 0) stamps[5] = global_ns();

@@ -56,10 +56,17 @@ template <typename T>
 __global__ void __launch_bounds__(kRowsPerBlock * 32)
 add_layernorm_kernel(int rows, int width, const T* __restrict__ x, int64_t ldx, const T* __restrict__ res, int64_t ldr,
                      const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ y, int64_t ldy) {
-  pdl_wait();
-  pdl_launch_dependents();
   const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  // gamma / beta are weights: they do not depend on the previous kernel, so they are fetched before the PDL wait
+  float g[kMaxChunks][8], b[kMaxChunks][8];
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int col = (lane + 32 * c) * 8;
+    if (col < width) { Vec8<float>::load(gamma + col, g[c]); Vec8<float>::load(beta + col, b[c]); }
+  }
+  pdl_wait();
+  pdl_launch_dependents();
   if (row >= rows) return;
   float v[kMaxChunks][8];
 #pragma unroll
@@ -75,7 +82,32 @@ add_layernorm_kernel(int rows, int width, const T* __restrict__ x, int64_t ldx, 
       }
     }
   }
-  ln_finish<T>(v, width, lane, gamma, beta, y + (int64_t)row * ldy);
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c)
+    if ((lane + 32 * c) * 8 < width)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[c][j];
+  const float mean = warp_sum(s) / (float)width;
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c)
+    if ((lane + 32 * c) * 8 < width)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { float d = v[c][j] - mean; q += d * d; }
+  const float var = warp_sum(q) / (float)width;
+  const float denom = sqrtf(var + kLnEps);
+  T* yrow = y + (int64_t)row * ldy;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int col = (lane + 32 * c) * 8;
+    if (col < width) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = g[c][j] * ((v[c][j] - mean) / denom) + b[c][j];
+      Vec8<T>::store(yrow + col, o);
+    }
+  }
 }
 
 template <typename T>

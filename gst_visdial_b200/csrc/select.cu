@@ -179,57 +179,83 @@ __device__ void hyp_add(const BeamBuffers& bb, int b, int K, int T, const int32_
   }
 }
 
-__global__ void beam_step_kernel(BeamBuffers bb, int B, int K, int T, int V, int nsel, const float* __restrict__ sel_val,
-                                 const int32_t* __restrict__ sel_idx, int eos, int32_t* out_beam_idx, int32_t* out_tokens,
-                                 float* out_scores) {
+// One warp per image.  The K x nsel per-row candidates are loaded in parallel, ranked in parallel by
+// (score desc, beam * V + token asc) - all pairs are distinct, so the rank is a permutation - and lane 0 then walks the
+// best 2K in order exactly like BeamSearchScorer.process; the token histories are gathered by all lanes.
+constexpr int kBeamWarps = 4;
+__global__ void __launch_bounds__(kBeamWarps * 32)
+beam_step_kernel(BeamBuffers bb, int B, int K, int T, int V, int nsel, const float* __restrict__ sel_val,
+                 const int32_t* __restrict__ sel_idx, int eos, int32_t* out_beam_idx, int32_t* out_tokens, float* out_scores) {
+  __shared__ float s_val[kBeamWarps][128];
+  __shared__ int s_flat[kBeamWarps][128];
+  __shared__ int s_order[kBeamWarps][16];
+  __shared__ float nb_s[kBeamWarps][8];
+  __shared__ int nb_tok[kBeamWarps][8], nb_par[kBeamWarps][8];
   pdl_wait();
   pdl_launch_dependents();
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kBeamWarps + warp;
   if (b >= B) return;
   const int t = *bb.d_step;
   const int cur_len = t + 1;
   const int32_t* src = bb.tokens + (int64_t)(t & 1) * B * K * T + (int64_t)b * K * T;
   int32_t* dst = bb.tokens + (int64_t)((t + 1) & 1) * B * K * T + (int64_t)b * K * T;
-  float nb_s[8]; int nb_tok[8], nb_par[8];
-  for (int k = 0; k < K; ++k) { nb_s[k] = 0.f; nb_tok[k] = 0; nb_par[k] = 0; }
-  if (!bb.done[b]) {
-    int head[8];
-    for (int k = 0; k < K; ++k) head[k] = 0;
-    int n = 0;
-    float best_sum = 0.f;
-    for (int rank = 0; rank < 2 * K; ++rank) {
-      // next candidate of the K-way merge, ordered by (score desc, beam*V + token asc)
-      int bk = -1; float bv = 0.f; int bt = 0;
-      for (int k = 0; k < K; ++k) {
-        if (head[k] >= nsel) continue;
-        const float v = sel_val[((int64_t)b * K + k) * nsel + head[k]];
-        const int tk = sel_idx[((int64_t)b * K + k) * nsel + head[k]];
-        if (bk < 0 || v > bv) { bk = k; bv = v; bt = tk; }     // equal score: the lower beam (lower flat index) stays
-      }
-      ++head[bk];
-      if (rank == 0) best_sum = bv;
-      if (bt == eos) {
-        if (rank >= K) continue;
-        hyp_add(bb, b, K, T, src + (int64_t)bk * T, t, bv, cur_len);
-      } else {
-        nb_s[n] = bv; nb_tok[n] = bt; nb_par[n] = bk; ++n;
-      }
-      if (n == K) break;
+  const int n = K * nsel;                      // <= 8 * 16 = 128
+  if (lane < 8) { nb_s[warp][lane] = 0.f; nb_tok[warp][lane] = 0; nb_par[warp][lane] = 0; }
+  const bool active = !bb.done[b];
+  if (active) {
+    for (int c = lane; c < n; c += 32) {
+      const int beam = c / nsel;
+      s_val[warp][c] = sel_val[(int64_t)b * n + c];
+      s_flat[warp][c] = beam * V + sel_idx[(int64_t)b * n + c];
     }
-    if (bb.hyp_count[b] >= K) {
-      const double cur = (double)best_sum / (double)cur_len;
-      if (bb.hyp_worst[b] >= cur) bb.done[b] = 1;
+    __syncwarp();
+    for (int c = lane; c < n; c += 32) {
+      const float v = s_val[warp][c]; const int f = s_flat[warp][c];
+      int rank = 0;
+      for (int o = 0; o < n; ++o) {
+        const float ov = s_val[warp][o]; const int of = s_flat[warp][o];
+        rank += (ov > v || (ov == v && of < f)) ? 1 : 0;
+      }
+      if (rank < 2 * K) s_order[warp][rank] = c;
     }
+    __syncwarp();
+    if (lane == 0) {
+      int cnt = 0;
+      const float best_sum = s_val[warp][s_order[warp][0]];
+      for (int rank = 0; rank < 2 * K; ++rank) {
+        const int c = s_order[warp][rank];
+        const float v = s_val[warp][c];
+        const int f = s_flat[warp][c];
+        const int bk = f / V, bt = f - bk * V;
+        if (bt == eos) {
+          if (rank >= K) continue;
+          hyp_add(bb, b, K, T, src + (int64_t)bk * T, t, v, cur_len);
+        } else {
+          nb_s[warp][cnt] = v; nb_tok[warp][cnt] = bt; nb_par[warp][cnt] = bk; ++cnt;
+        }
+        if (cnt == K) break;
+      }
+      if (bb.hyp_count[b] >= K) {
+        const double cur = (double)best_sum / (double)cur_len;
+        if (bb.hyp_worst[b] >= cur) bb.done[b] = 1;
+      }
+    }
+    __syncwarp();
   }
-  for (int k = 0; k < K; ++k) {
-    for (int j = 0; j < T; ++j) dst[k * T + j] = src[nb_par[k] * T + j];
-    if (t < T) dst[k * T + t] = nb_tok[k];
-    bb.beam_scores[b * K + k] = nb_s[k];
-    bb.cur_tokens[b * K + k] = nb_tok[k];
-    bb.beam_idx[b * K + k] = nb_par[k];
-    if (out_beam_idx) out_beam_idx[b * K + k] = nb_par[k];
-    if (out_tokens) out_tokens[b * K + k] = nb_tok[k];
-    if (out_scores) out_scores[b * K + k] = nb_s[k];
+  __syncwarp();
+  for (int i = lane; i < K * T; i += 32) {
+    const int k = i / T, j = i - k * T;
+    dst[i] = (j == t) ? nb_tok[warp][k] : src[nb_par[warp][k] * T + j];
+  }
+  if (lane < K) {
+    const int k = lane;
+    bb.beam_scores[b * K + k] = nb_s[warp][k];
+    bb.cur_tokens[b * K + k] = nb_tok[warp][k];
+    bb.beam_idx[b * K + k] = nb_par[warp][k];
+    if (out_beam_idx) out_beam_idx[b * K + k] = nb_par[warp][k];
+    if (out_tokens) out_tokens[b * K + k] = nb_tok[warp][k];
+    if (out_scores) out_scores[b * K + k] = nb_s[warp][k];
   }
 }
 
@@ -462,7 +488,7 @@ int launch_beam_step(const BeamBuffers& bb, int B, int K, int T, int V, int nsel
                      const int32_t* sel_idx, int eos, int32_t* out_beam_idx, int32_t* out_tokens, float* out_scores,
                      cudaStream_t stream) {
   if (K > 8 || T > kHypMaxT) throw std::runtime_error("beam_step: K <= 8 and T <= 32");
-  launch_k(beam_step_kernel, dim3((B + 31) / 32), dim3(32), 0, stream, bb, B, K, T, V, nsel, sel_val, sel_idx, eos, out_beam_idx, out_tokens, out_scores);
+  launch_k(beam_step_kernel, dim3((B + kBeamWarps - 1) / kBeamWarps), dim3(kBeamWarps * 32), 0, stream, bb, B, K, T, V, nsel, sel_val, sel_idx, eos, out_beam_idx, out_tokens, out_scores);
   return 1;
 }
 int launch_beam_finalize(const BeamBuffers& bb, int B, int K, int T, int eos, int64_t* out_ids, float* out_scores,
