@@ -170,9 +170,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 template <int BN> struct TileCfg {
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  // k-chunks (64 elements each) per pipeline stage.  The narrow tiles serve the M <= 384 decode GEMMs, whose main loop is
+  // bound by the RATE of TMA operations issued by one thread (~0.13 us each), not by bytes: one 3-D box
+  // {64, rows, 4 chunks} moves four k-blocks per operation.
+  static constexpr int kCK = BN <= 64 ? 4 : 1;
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 2);
+  static constexpr int kAChunk = BM * BK * 2;                  // one 128-row x 64-element SW128 tile
+  static constexpr int kBChunk = BN * BK * 2;
+  static constexpr int kABytes = kAChunk * kCK;
+  static constexpr int kBBytes = kBChunk * kCK;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // power of two for BN in {16,32,64,128,256}
   static constexpr int kBarBytes = 256;
   static constexpr int kStageWords = 32 * 33;                   // per epilogue warp: 32 rows x 32 words, padded rows
@@ -394,7 +400,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const int tiles_n = (p.N + BN - 1) / BN;
   const int tiles_m = p.hm_tpi > 0 ? p.hm_B * p.hm_tpi : (p.M + BM - 1) / BM;
   const int num_tiles = tiles_m * tiles_n;
-  const int num_kb = (p.K + BK - 1) / BK;
+  constexpr int kCK = Cfg::kCK;
+  const int num_kb = (p.K + BK * kCK - 1) / (BK * kCK);      // pipeline stages per tile
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -417,8 +424,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       pdl_launch_dependents();                       // the next kernel may start its prologue / weight prefetch
       int stage = 0; uint32_t phase = 0;
       bool first = true;
+      auto load_b = [&](int st, int kb, int n_blk) {
+        if constexpr (kCK > 1) tma_load_3d(b_base + st * Cfg::kBBytes, &tm_b, 0, n_blk * BN, kb * kCK, full_bar(st));
+        else tma_load_2d(b_base + st * Cfg::kBBytes, &tm_b, kb * BK, n_blk * BN, full_bar(st));
+      };
       auto load_a = [&](int st, int kb, int m_blk) {
-        if (p.hm_tpi > 0) {
+        if constexpr (kCK > 1) {
+          tma_load_3d(a_base + st * Cfg::kABytes, &tm_a, 0, m_blk * BM, kb * kCK, full_bar(st));
+        } else if (p.hm_tpi > 0) {
           const int img = m_blk / p.hm_tpi;
           tma_load_3d(a_base + st * Cfg::kABytes, &tm_a, kb * BK, (m_blk - img * p.hm_tpi) * BM, img, full_bar(st));
         } else {
@@ -435,7 +448,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           const int pre = num_kb < kStages ? num_kb : kStages;
           for (int st = 0; st < pre; ++st) {
             mbar_arrive_expect_tx(full_bar(st), Cfg::kABytes + Cfg::kBBytes);
-            tma_load_2d(b_base + st * Cfg::kBBytes, &tm_b, st * BK, n_blk * BN, full_bar(st));
+            load_b(st, st, n_blk);
           }
           pdl_wait();
           if (stamps) stamps[2] = global_ns();
@@ -447,7 +460,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), Cfg::kABytes + Cfg::kBBytes);
           load_a(stage, kb, m_blk);
-          tma_load_2d(b_base + stage * Cfg::kBBytes, &tm_b, kb * BK, n_blk * BN, full_bar(stage));
+          load_b(stage, kb, n_blk);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -466,12 +479,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           mbar_wait(full_bar(stage), phase);         // TMA bytes have landed
           tc_fence_after();
           if (stamps && iter == 0 && kb == 0) stamps[3] = global_ns();
-          const uint64_t a_desc = make_smem_desc(a_base + stage * Cfg::kABytes);
-          const uint64_t b_desc = make_smem_desc(b_base + stage * Cfg::kBBytes);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            if (p.dbg != 3) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int ck = 0; ck < kCK; ++ck) {
+            const uint64_t a_desc = make_smem_desc(a_base + stage * Cfg::kABytes + ck * Cfg::kAChunk);
+            const uint64_t b_desc = make_smem_desc(b_base + stage * Cfg::kBBytes + ck * Cfg::kBChunk);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+              if (p.dbg != 3) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | ck | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(empty_bar(stage));             // frees the smem slot when these MMAs retire
           if (kb == num_kb - 1) { umma_commit(tfull_bar(as)); if (stamps) stamps[4] = global_ns(); }
@@ -603,6 +619,18 @@ const CUtensorMap& get_map(const void* ptr, int64_t rows, int64_t cols, int64_t 
   return cached_map(key, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+// Operand viewed as [K/64 chunks][rows][64]: one box = 64 elements x box_rows rows x `chunks` consecutive k-chunks, each chunk
+// landing as its own 128-byte-swizzled tile (row stride 128 B) - the layout the UMMA descriptors expect.
+const CUtensorMap& get_map_k3(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int chunks) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0 || cols % BK != 0)
+    throw std::runtime_error("gemm_tc: chunked operand needs 16-byte alignment, ld % 8 == 0 and K % 64 == 0");
+  MapKey key{ptr, rows, cols, ld, box_rows, BK, 2, 5, chunks, 0};
+  cuuint64_t gdim[3] = {(cuuint64_t)BK, (cuuint64_t)rows, (cuuint64_t)(cols / BK)};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)BK * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, (cuuint32_t)chunks};
+  return cached_map(key, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 // Output map for the TMA-store epilogue: [M, N] row-major with box = box_cols x 128 rows.
 const CUtensorMap& get_map_c(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int esz, int box_cols) {
   MapKey key{ptr, rows, cols, ld, BM, box_cols, esz, 1, 0, 0};
@@ -650,8 +678,8 @@ void launch_cfg(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
     attr_set = true;
   }
   GemmArgs a = a_in;
-  const CUtensorMap* ma_ptr = &get_map(a.A, a.M, a.K, a.lda, BM);
-  const CUtensorMap& mb = get_map(a.W, a.N, a.K, a.ldw, BN);
+  const CUtensorMap* ma_ptr = Cfg::kCK > 1 ? &get_map_k3(a.A, a.M, a.K, a.lda, BM, Cfg::kCK) : &get_map(a.A, a.M, a.K, a.lda, BM);
+  const CUtensorMap& mb = Cfg::kCK > 1 ? get_map_k3(a.W, a.N, a.K, a.ldw, BN, Cfg::kCK) : get_map(a.W, a.N, a.K, a.ldw, BN);
   // TMA-store epilogue when the output is expressible as a tensor map; otherwise the generic register/shared path
   const int esz = a.out_f32 ? 4 : 2;
   const int cw = 32;                                  // columns per TMA-store box (bf16: 64-byte rows, fp32: 128-byte rows)
@@ -661,7 +689,7 @@ void launch_cfg(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
   static const bool no_tma_hm = getenv("GSTVD_GEMM_NO_TMA_HM") != nullptr;
   if (!no_tma_store && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0) {
     if (a.hm_D > 0) {
-      if (!no_tma_hm && !a.out_f32 && a.hm_D % cw == 0 && a.M == a.hm_B * a.hm_L) {
+      if (!no_tma_hm && Cfg::kCK == 1 && !a.out_f32 && a.hm_D % cw == 0 && a.M == a.hm_B * a.hm_L) {
         const int64_t LB = (int64_t)(a.N / (a.hm_D * a.hm_G)) * a.hm_B;
         mc = &get_map_hm3(a.C, a.hm_D, a.hm_L, LB * a.hm_G, cw);
         a.hm_tpi = (a.hm_L + BM - 1) / BM;
@@ -709,6 +737,7 @@ int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
     if (a.N >= cand[i] && tiles_m * ((a.N + cand[i] - 1) / cand[i]) >= num_sms) { bn = cand[i]; break; }
   }
   if (bn_env) bn = bn_env;
+  if (bn <= 64 && a.K % BK != 0) bn = 128;               // the chunked (3-D box) operand view needs whole 64-element chunks
   switch (bn) {
     case 256: launch_cfg<256>(a, num_sms, stream); break;
     case 128: launch_cfg<128>(a, num_sms, stream); break;
