@@ -44,6 +44,8 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(AttnArgs p, int lk_p
   bf16* Vs = Ks + (size_t)lk_pad * LD;
   float* madd = reinterpret_cast<float*>(Vs + (size_t)lk_pad * LD);
 
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kQTile;
   const int bkv = b / p.kv_batch_div;
@@ -193,7 +195,7 @@ void launch_d(const AttnArgs& a, cudaStream_t stream) {
     configured = 200 * 1024;
   }
   dim3 grid((a.Lq + kQTile - 1) / kQTile, a.H, a.B);
-  attention_mma_kernel<D><<<grid, 128, smem, stream>>>(a, lk_pad);
+  launch_k(attention_mma_kernel<D>, grid, dim3(128), smem, stream, a, lk_pad);
 }
 
 }  // namespace

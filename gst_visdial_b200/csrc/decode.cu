@@ -9,6 +9,7 @@
 //                    (models/visual_dialog_decoder.py:29-31,177-181)
 // Layouts:  self cache  [layer][k|v][image][position][beam][hidden]   (a beam gather touches contiguous rows)
 //           cross cache [layer][image][k|v, head][position][head_dim]  (one contiguous block per (image, head))
+#include <cstdlib>
 #include <stdexcept>
 
 #include "common.cuh"
@@ -285,6 +286,176 @@ dec_cross_attn_kernel(DecodeGeom g, const T* __restrict__ q, const T* __restrict
   }
 }
 
+// ---- tensor-core decode cross-attention (bf16, head_dim 64, <= 8 beams, Le <= 320) ----------------------------------
+// One CTA of 4 warps per (image, head).  Every K / V byte is loaded from global exactly once, as a 16-byte load, straight
+// into mma.sync fragments - no shared-memory staging of K or V:
+//   scores  S = Q K^T : the 8 keys of a tile are the N dimension, the beams the (zero padded) M rows.  The reduction index
+//            (head dim) may be permuted freely as long as A and B agree, so the natural 16-byte chunk a lane loads from a key
+//            row (8 consecutive dims) is used as the lane's two k-slot pairs of two k-steps; Q is loaded the same way.
+//   context O = P V   : V rows are loaded the same way and transposed in registers with movmatrix (8x8 b16), which yields
+//            B fragments whose N index is a permutation of the head dim; the permutation is chosen so that each lane ends up
+//            with 8 CONSECUTIVE output dims.
+// Softmax is the exact two-pass softmax over all keys (scores in shared memory), like the reference.
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  const uint32_t z = 0u;   // rows 8..15 of the A tile (beams that do not exist) are zero
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(z), "r"(a2), "r"(z), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+
+constexpr int kXMaxTiles = 10;   // key tiles (8 keys) per warp: 4 warps x 10 x 8 = 320 keys
+constexpr int kXMaxGroups = 5;   // 16-key groups per warp
+
+__global__ void __launch_bounds__(128, 6)
+dec_cross_mma_kernel(DecodeGeom g, const bf16* __restrict__ q, const bf16* __restrict__ kv_layer, const float* __restrict__ enc_mask,
+                     bf16* __restrict__ out) {
+  constexpr int D = 64;
+  extern __shared__ __align__(16) uint8_t xsm[];
+  const int Le = g.Le, LeP = (Le + 15) & ~15;
+  float* S = reinterpret_cast<float*>(xsm);                       // [8][LeP]
+  float* madd = S + 8 * LeP;                                      // [LeP]
+  float* part = madd + LeP;                                       // [4][8][64]
+  bf16* P = reinterpret_cast<bf16*>(part + 4 * 8 * D);            // [8][LeP]
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int beam = lane >> 2, p4 = lane & 3;
+  const bf16* Kp = kv_layer + ((int64_t)b * 2 * g.heads + h) * Le * D;
+  const bf16* Vp = kv_layer + ((int64_t)b * 2 * g.heads + g.heads + h) * Le * D;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  const int ntiles = (Le + 7) >> 3, ngroups = LeP >> 4;
+
+  // K fragments of this warp's first key tiles: independent of the previous kernel (written at prefill), issued before the
+  // PDL wait.  Tiles are processed in two batches of 5 to keep the register count low enough for 6 CTAs per SM (one wave).
+  constexpr int kKB = kXMaxTiles / 2;
+  uint4 kreg[kKB][2];
+  auto load_k = [&](int i0) {
+#pragma unroll
+    for (int i = 0; i < kKB; ++i) {
+      const int t = warp + 4 * (i0 + i);
+      const int key = t * 8 + beam;                               // lane / 4 = key inside the tile
+      if (t < ntiles && key < Le) {
+        const bf16* kp = Kp + (int64_t)key * D + p4 * 8;
+        kreg[i][0] = *reinterpret_cast<const uint4*>(kp);
+        kreg[i][1] = *reinterpret_cast<const uint4*>(kp + 32);
+      } else { kreg[i][0] = zero4; kreg[i][1] = zero4; }
+    }
+  };
+  load_k(0);
+  for (int j = threadIdx.x; j < LeP; j += blockDim.x)
+    madd[j] = (j < Le) ? (1.0f - (enc_mask ? enc_mask[(int64_t)b * Le + j] : 1.f)) * -1e9f : 0.f;
+  pdl_wait();
+  uint4 qlo = zero4, qhi = zero4;
+  if (beam < g.K) {
+    const bf16* qp = q + ((int64_t)(b * g.K + beam)) * g.H + h * D + p4 * 8;
+    qlo = *reinterpret_cast<const uint4*>(qp);
+    qhi = *reinterpret_cast<const uint4*>(qp + 32);
+  }
+  __syncthreads();                                                // madd visible
+  // ---- scores ----
+#pragma unroll
+  for (int i0 = 0; i0 < kXMaxTiles; i0 += kKB) {
+    if (i0 > 0) load_k(i0);
+#pragma unroll
+    for (int i = 0; i < kKB; ++i) {
+      const int t = warp + 4 * (i0 + i);
+      if (t < ntiles) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_bf16_16816(c, qlo.x, qlo.y, kreg[i][0].x, kreg[i][0].y);
+        mma_bf16_16816(c, qlo.z, qlo.w, kreg[i][0].z, kreg[i][0].w);
+        mma_bf16_16816(c, qhi.x, qhi.y, kreg[i][1].x, kreg[i][1].y);
+        mma_bf16_16816(c, qhi.z, qhi.w, kreg[i][1].z, kreg[i][1].w);
+        const int key0 = t * 8 + p4 * 2;                          // C fragment: row = lane/4 (beam), cols = (lane%4)*2 + {0,1}
+        if (beam < g.K) {
+          if (key0 < Le) S[beam * LeP + key0] = c[0] / 8.0f + madd[key0];
+          if (key0 + 1 < Le) S[beam * LeP + key0 + 1] = c[1] / 8.0f + madd[key0 + 1];
+        }
+      }
+    }
+  }
+  // V rows of this warp's first 16-key groups: in flight while the softmax runs
+  constexpr int kVB = 3;
+  uint4 vreg[kVB][2][2];                                          // [group][8-key half][dim half]
+  auto load_v = [&](int i0) {
+#pragma unroll
+    for (int i = 0; i < kVB; ++i) {
+#pragma unroll
+      for (int kh = 0; kh < 2; ++kh) {
+        const int G = warp + 4 * (i0 + i);
+        const int key = G * 16 + kh * 8 + beam;
+        if (i0 + i < kXMaxGroups && G < ngroups && key < Le) {
+          const bf16* vp = Vp + (int64_t)key * D + p4 * 8;
+          vreg[i][kh][0] = *reinterpret_cast<const uint4*>(vp);
+          vreg[i][kh][1] = *reinterpret_cast<const uint4*>(vp + 32);
+        } else { vreg[i][kh][0] = zero4; vreg[i][kh][1] = zero4; }
+      }
+    }
+  };
+  load_v(0);
+  __syncthreads();
+  // ---- exact softmax, one warp per beam; probabilities stored as bf16 (zero past Le) ----
+  for (int k = warp; k < 8; k += 4) {
+    float* Sr = S + k * LeP;
+    bf16* Pr = P + k * LeP;
+    if (k < g.K) {
+      float mx = -INFINITY;
+      for (int j = lane; j < Le; j += 32) mx = fmaxf(mx, Sr[j]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int j = lane; j < Le; j += 32) { const float e = expf(Sr[j] - mx); Sr[j] = e; sum += e; }
+      sum = warp_sum(sum);
+      for (int j = lane; j < LeP; j += 32) Pr[j] = __float2bfloat16_rn(j < Le ? Sr[j] / sum : 0.f);
+    } else {
+      for (int j = lane; j < LeP; j += 32) Pr[j] = __float2bfloat16_rn(0.f);
+    }
+  }
+  __syncthreads();
+  // ---- context ----
+  float o[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+#pragma unroll
+  for (int i0 = 0; i0 < kXMaxGroups; i0 += kVB) {
+    if (i0 > 0) load_v(i0);
+#pragma unroll
+    for (int i = 0; i < kVB; ++i) {
+      const int G = warp + 4 * (i0 + i);
+      if (i0 + i < kXMaxGroups && G < ngroups) {
+        const uint32_t* prow = reinterpret_cast<const uint32_t*>(P + beam * LeP + G * 16);
+        const uint32_t a0 = prow[p4], a2 = prow[4 + p4];          // keys 16G + (lane%4)*2 + {0,1} and + 8
+#pragma unroll
+        for (int dh = 0; dh < 2; ++dh) {
+          const uint4 v0 = vreg[i][0][dh], v1 = vreg[i][1][dh];
+          const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w}, w1[4] = {v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            mma_bf16_16816(o[dh * 4 + j], a0, a2, movmatrix_trans(w0[j]), movmatrix_trans(w1[j]));
+        }
+      }
+    }
+  }
+  // lane holds O[beam = lane/4][dims dh*32 + (lane%4)*8 + 2j + {0,1}] summed over this warp's keys; reduce over warps
+#pragma unroll
+  for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float* pp = part + ((warp * 8 + beam) * D) + dh * 32 + p4 * 8 + 2 * j;
+      pp[0] = o[dh * 4 + j][0];
+      pp[1] = o[dh * 4 + j][1];
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < g.K * D; i += blockDim.x) {
+    const int k = i / D, d = i - k * D;
+    const float v = (part[(0 * 8 + k) * D + d] + part[(1 * 8 + k) * D + d]) + (part[(2 * 8 + k) * D + d] + part[(3 * 8 + k) * D + d]);
+    out[((int64_t)(b * g.K + k)) * g.H + h * D + d] = __float2bfloat16_rn(v);
+  }
+}
+
 template <typename T, int KB>
 void launch_cross_kb(const DecodeGeom& g, const T* q, const T* kv_layer, const float* enc_mask, T* out, cudaStream_t stream) {
   const size_t s_elems = ((size_t)KB * g.Le + 3) & ~size_t(3);          // keeps the query tile 16-byte aligned
@@ -353,6 +524,12 @@ int launch_dec_cross_attn(int dtype, const DecodeGeom& g, int layer, const void*
   const int64_t esz = dtype == kF32 ? 4 : 2;
   const int64_t per_image = (int64_t)2 * g.heads * g.Le * g.D;
   const char* kbase = (const char*)cross_cache + ((int64_t)layer * g.B) * per_image * esz;
+  if (dtype == kBF16 && g.D == 64 && g.K <= 8 && g.Le <= 4 * kXMaxTiles * 8 && getenv("GSTVD_CROSS_SIMT") == nullptr) {
+    const int LeP = (g.Le + 15) & ~15;
+    const size_t smem = (size_t)(8 * LeP + LeP + 4 * 8 * 64) * sizeof(float) + (size_t)8 * LeP * sizeof(bf16);
+    launch_k(dec_cross_mma_kernel, dim3(g.heads, g.B), dim3(128), smem, stream, g, (const bf16*)q, (const bf16*)kbase, enc_mask, (bf16*)out);
+    return 1;
+  }
   if (g.D == 64 && g.K <= 8 && g.Le <= 1024) {
     if (dtype == kF32) launch_cross_t<float>(g, q, kbase, enc_mask, out, stream);
     else launch_cross_t<bf16>(g, q, kbase, enc_mask, out, stream);
