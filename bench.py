@@ -231,8 +231,6 @@ def main():
             batch, ques = (sl["host"], sl["questions_h"]) if from_host else (sl["dev_batch"], sl["questions_d"])
             res = generate_dialogs(sl["model"], batch, questions=ques, num_rounds=a.rounds, a_kwargs=akw, with_ppl=False, device=dev)
             ans, abn = res.answers, res.abnormal
-            if world > 1:                               # the only collective: final gather of ids (+ flags) over NVLink
-                ans, abn = D.gather_results([ans, abn], counts)
             if to_host:                                 # device -> pinned host, asynchronous on this slot's stream
                 if "out_ans" not in sl:
                     sl["out_ans"] = torch.empty(ans.shape, dtype=ans.dtype).pin_memory()
@@ -282,6 +280,17 @@ def main():
             for th in threads:
                 th.join()
         out = outs[0]
+        if world > 1:
+            # The only collective of the job: ONE final all_gather (NCCL over NVLink) of the generated token ids and flags
+            # of this rank's last batch per stream, issued from the main thread after every stream has drained (collectives
+            # issued concurrently from several host threads would not be ordered consistently across ranks).
+            for sl in slots:
+                cur.wait_stream(sl["stream"])
+            mine = [o for o in outs if o is not None]
+            ans = torch.cat([o[0].to(dev) for o in mine], 0)
+            abn = torch.cat([o[1].to(dev) for o in mine], 0)
+            g_ans, g_abn = D.gather_results([ans, abn], [ans.shape[0]] * world)
+            out = (g_ans, g_abn)
         host_ms[0] = (time.perf_counter() - t_host) * 1e3 / steps      # CPU wall time to ENQUEUE one step (no device wait inside)
         for sl in slots:
             cur.wait_stream(sl["stream"])
