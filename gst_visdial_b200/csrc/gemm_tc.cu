@@ -730,11 +730,19 @@ int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
   if (a.hm_D > 0 && (a.hm_D % 32 != 0)) throw std::runtime_error("gemm_tc: head-major scatter needs head_dim % 32 == 0");
   gemm_tc_init();
   const int tiles_m = (a.M + BM - 1) / BM;
-  // largest N tile that still gives every SM a tile; small problems fall through to the narrowest tile
   int bn = 32;
-  const int cand[3] = {256, 128, 64};
-  for (int i = 0; i < 3; ++i) {
-    if (a.N >= cand[i] && tiles_m * ((a.N + cand[i] - 1) / cand[i]) >= num_sms) { bn = cand[i]; break; }
+  const int cand[4] = {256, 128, 64, 32};
+  if (tiles_m <= 4) {
+    // skinny (decode) problems are latency-bound: prefer ONE wave - the narrowest tile whose tile count still fits the SMs
+    bn = 256;
+    for (int i = 3; i >= 0; --i) {
+      if (tiles_m * ((a.N + cand[i] - 1) / cand[i]) <= num_sms) { bn = cand[i]; break; }
+    }
+  } else {
+    // largest N tile that still gives every SM a tile; small problems fall through to the narrowest tile
+    for (int i = 0; i < 3; ++i) {
+      if (a.N >= cand[i] && tiles_m * ((a.N + cand[i] - 1) / cand[i]) >= num_sms) { bn = cand[i]; break; }
+    }
   }
   if (bn_env) bn = bn_env;
   if (bn <= 64 && a.K % BK != 0) bn = 128;               // the chunked (3-D box) operand view needs whole 64-element chunks
