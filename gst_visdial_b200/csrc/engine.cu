@@ -626,11 +626,15 @@ void do_generate(gstvd_ctx* c, int B, const gstvd_gen_params& gp, const int64_t*
   else c->launches += launch_sample_finalize(B, T, 102, (const int32_t*)c->seq.p, out_ids, s);
 }
 
+// `options` decoder sequences per image share that image's cross-attention K/V (evaluate_gen.py:62-107 re-encodes the same
+// (image, history) once per answer option; here it is encoded once).  B = sequences = images * options.
 void do_score(gstvd_ctx* c, int B, int L, int64_t* dec_ids, const float* dec_mask, const int64_t* labels, float* out_loss,
-              float* out_logits, cudaStream_t s) {
+              float* out_logits, cudaStream_t s, int options = 1) {
   check_ready(c);
   if (c->dec_layers == 0) throw StateError("score: encoder-only context");
-  if (c->cross_B != B) throw StateError(fmt("score: cross K/V prefilled for %d images, asked for %d", c->cross_B, B));
+  if (options < 1 || B % options != 0) throw InvalidArg("score: sequences must be a multiple of options");
+  if (B > c->B_max) throw InvalidArg(fmt("score: %d sequences exceed the context capacity %d", B, c->B_max));
+  if (c->cross_B != B / options) throw StateError(fmt("score: cross K/V prefilled for %d images, asked for %d", c->cross_B, B / options));
   if (L < 1 || L > c->Ldec_max || L > c->cfg.max_position_embeddings) throw InvalidArg("score: L out of range");
   if (!dec_ids) throw InvalidArg("score: dec_ids is NULL");
   Exec X{c, s};
@@ -653,13 +657,13 @@ void do_score(gstvd_ctx* c, int B, int L, int64_t* dec_ids, const float* dec_mas
     X.gemm(c->da.p, H, Ly.cq, c->dqc.p, H, M);
     {
       AttnArgs a;
-      const char* kbase = (const char*)c->cross_cache.p + (size_t)l * B * per_image * c->esz;
+      const char* kbase = (const char*)c->cross_cache.p + (size_t)l * (B / options) * per_image * c->esz;
       a.q = c->dqc.p; a.q_bs = (int64_t)L * H; a.q_hs = D; a.q_rs = H;
       a.k = kbase; a.k_bs = per_image; a.k_hs = (int64_t)Le * D; a.k_rs = D;
       a.v = kbase + (size_t)c->dec_heads * Le * D * c->esz; a.v_bs = per_image; a.v_hs = a.k_hs; a.v_rs = D;
       a.o = c->dctx.p; a.o_bs = (int64_t)L * H; a.o_hs = D; a.o_rs = H;
       a.kmask = (const float*)c->fused_mask.p; a.kmask_bs = Le; a.neg = -1e9f; a.causal = 0;
-      a.B = B; a.H = c->dec_heads; a.Lq = L; a.Lk = Le; a.D = D; a.kv_batch_div = 1;
+      a.B = B; a.H = c->dec_heads; a.Lq = L; a.Lk = Le; a.D = D; a.kv_batch_div = options;
       X.run_attention(a);
     }
     X.gemm(c->dctx.p, H, Ly.co, c->dtmp.p, H, M);
@@ -857,6 +861,12 @@ int gstvd_score(gstvd_ctx* c, int B, int L, int64_t* dec_ids, const float* dec_m
                 float* out_logits, void* stream) {
   if (!c) { g_last_error = "gstvd_score: NULL context"; return GSTVD_ERR_INVALID; }
   return guarded(c, [&] { do_score(c, B, L, dec_ids, dec_mask, labels, out_loss, out_logits, (cudaStream_t)stream); });
+}
+
+int gstvd_score_options(gstvd_ctx* c, int n_images, int options, int L, int64_t* dec_ids, const float* dec_mask, const int64_t* labels,
+                        float* out_loss, float* out_logits, void* stream) {
+  if (!c) { g_last_error = "gstvd_score_options: NULL context"; return GSTVD_ERR_INVALID; }
+  return guarded(c, [&] { do_score(c, n_images * options, L, dec_ids, dec_mask, labels, out_loss, out_logits, (cudaStream_t)stream, options); });
 }
 
 int gstvd_reorder_cache(gstvd_ctx* c, int B, int K, int len, const int32_t* beam_idx, void* stream) {

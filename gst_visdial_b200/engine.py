@@ -170,8 +170,9 @@ class Engine:
                                                 self._stream()))
         return (out, scores) if want_scores else out
 
-    def score(self, dec_ids, dec_mask=None, labels=None, want_logits=False, want_loss=True):
-        """``dec_ids`` (int64, on the engine's device, contiguous) is mutated in place when ``labels`` is None."""
+    def score(self, dec_ids, dec_mask=None, labels=None, want_logits=False, want_loss=True, options_per_image=1):
+        """``dec_ids`` (int64, on the engine's device, contiguous) is mutated in place when ``labels`` is None.
+        ``options_per_image`` > 1: rows are option-major per image and share the image's cross-attention K/V."""
         if dec_ids.device != self.device or dec_ids.dtype != torch.int64 or not dec_ids.is_contiguous():
             raise ValueError("score: dec_ids must be a contiguous int64 tensor on the engine's device (it is updated in place)")
         B, L = dec_ids.shape
@@ -180,7 +181,11 @@ class Engine:
         V = self.cfg.vocab_size
         loss = torch.empty(B, L, device=self.device, dtype=torch.float32) if want_loss else None
         logits = torch.empty(B, L, V, device=self.device, dtype=torch.float32) if want_logits else None
-        check(self.ctx, self.lib.gstvd_score(self.ctx, B, L, _ptr(dec_ids), _ptr(m), _ptr(lab), _ptr(loss), _ptr(logits), self._stream()))
+        if options_per_image > 1:
+            check(self.ctx, self.lib.gstvd_score_options(self.ctx, B // options_per_image, int(options_per_image), L, _ptr(dec_ids), _ptr(m),
+                                                         _ptr(lab), _ptr(loss), _ptr(logits), self._stream()))
+        else:
+            check(self.ctx, self.lib.gstvd_score(self.ctx, B, L, _ptr(dec_ids), _ptr(m), _ptr(lab), _ptr(loss), _ptr(logits), self._stream()))
         return loss, logits
 
     def reorder_cache(self, beam_idx: torch.Tensor, length: int):

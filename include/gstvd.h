@@ -155,6 +155,13 @@ int gstvd_generate(gstvd_ctx* ctx, int B, const gstvd_gen_params* params,
 int gstvd_score(gstvd_ctx* ctx, int B, int L, int64_t* dec_ids, const float* dec_mask, const int64_t* labels,
                 float* out_loss, float* out_logits, void* stream);
 
+/* Generative ranking (evaluate_gen.py:62-107): `options` candidate sequences per image are scored against ONE encoder pass /
+ * cross-attention K/V of that image (the reference re-encodes the same image and history for every option).
+ *   dec_ids / dec_mask / labels / out_loss / out_logits : as gstvd_score with B = n_images * options rows, option-major per image
+ *   n_images must equal the B of the last gstvd_prefill_cross; n_images * options <= config.max_batch */
+int gstvd_score_options(gstvd_ctx* ctx, int n_images, int options, int L, int64_t* dec_ids, const float* dec_mask,
+                        const int64_t* labels, float* out_loss, float* out_logits, void* stream);
+
 /* In-place beam reorder of the self-attention KV cache: cache[:, new_beam] = cache[:, beam_idx[new_beam]] for
  * every layer - the semantic of _reorder_cache / index_select(0, beam_idx) (models/visual_dialog_decoder.py:29-31,
  * :177-181).  beam_idx int32 [B, K] holds the parent beam (0..K-1) within each image; len = cached positions. */

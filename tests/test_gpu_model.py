@@ -338,3 +338,31 @@ def test_generate_cli_synthetic(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     out = json.load(open(tmp_path / "o.json"))
     assert len(out) == 5 and len(out[0]["dialog"]) == 2 and out[0]["dialog"][0]["answer_ppl"] > 0
+
+
+def test_generative_ranking_shares_encoder(tiny_fp32, tiny_cfgs, tiny_sd):
+    """f1 (evaluate_gen.py:62-107): O options per image scored against one encoder pass == scoring every option separately."""
+    from gst_visdial_b200.ranking import score_options
+    model, _ = tiny_fp32
+    enc_cfg, dec_cfg = tiny_cfgs
+    B, O, L = 2, 4, 12
+    b = history_batch(enc_cfg, 0, B)
+    g = torch.Generator().manual_seed(3)
+    opts = torch.zeros(B, O, L, dtype=torch.int64)
+    for i in range(B):
+        for o in range(O):
+            n = int(torch.randint(3, L - 1, (1,), generator=g))
+            opts[i, o, 0] = 101
+            opts[i, o, 1:n] = torch.randint(104, enc_cfg.vocab_size, (n - 1,), generator=g)
+            opts[i, o, n] = 102
+    scores = score_options(model, b, opts).cpu()
+    with torch.no_grad():
+        t, v = R.encoder(tiny_sd, enc_cfg, b["enc_input_ids"], b["enc_image_feat"], b["enc_image_loc"], b["enc_segments"], b["enc_att_mask"], b["enc_image_mask"])
+        eh, em = R.vlfusion(tiny_sd, t, v, b["enc_att_mask"], b["enc_image_mask"])
+        ids = opts.reshape(B * O, L)
+        labels = torch.zeros_like(ids); labels[:, :-1] = ids[:, 1:]
+        logits = R.lm_logits(tiny_sd, R.decoder_hidden(tiny_sd, dec_cfg, ids, (ids != 0).float(), eh.repeat_interleave(O, 0), em.repeat_interleave(O, 0)))
+        lp = torch.log_softmax(logits, -1).gather(-1, labels.unsqueeze(-1)).squeeze(-1) * (labels != 0).float()
+        ref = lp.sum(-1).reshape(B, O)
+    assert max_abs(scores, ref) < 2e-3
+    assert torch.equal(scores.argsort(-1), ref.argsort(-1))
