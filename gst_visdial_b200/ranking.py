@@ -36,3 +36,38 @@ def score_options(model, batch, option_ids: torch.Tensor, option_labels: torch.T
     mask = (ids != 0).float()
     loss, _ = eng.score(ids, mask, labels=labels, want_logits=False, options_per_image=O)
     return (-loss.sum(-1)).reshape(B, O)
+
+
+def answer_perplexity(model, batch, answer_ids: torch.Tensor, device=None) -> torch.Tensor:
+    """Teacher-forced perplexity of ``answer_ids`` int64 [B, L] (no leading [CLS], zero padded) under the model: the pass
+    of generate.py:183-209, which is also BASELINE config 4 (scoring (context, answer) pairs for -select_data).
+    ppl = exp(sum CE / count(ids != 0)); labels are the ids shifted left, so the first token is unscored and a generated
+    [SEP] counts in the numerator but not in the length (it is replaced by [PAD] in place before the count).  fp32 [B]."""
+    m = _unwrap(model)
+    dev = torch.device(device) if device is not None else next(m.parameters()).device
+    eng = m._engine(dev)
+    B = answer_ids.shape[0]
+    enc = eng.encode(batch["enc_input_ids"], batch["enc_image_feat"], batch["enc_image_loc"], batch["enc_segments"],
+                     batch["enc_att_mask"], batch["enc_image_mask"])
+    eng.prefill_cross(B, enc["Le"])
+    ids = answer_ids.to(device=dev, dtype=torch.int64).contiguous().clone()
+    mask = (ids != 0).float()
+    loss, _ = eng.score(ids, mask, labels=None, want_logits=False)      # shifts the labels and maps [SEP] -> [PAD] in ids
+    return torch.exp(loss.sum(-1) / (ids != 0).sum(-1))
+
+
+def select_mask(answer_ppl: torch.Tensor, threshold: float = 50) -> torch.Tensor:
+    """-select_data (dataloader/dataloader_cc12m_gen.py:193-199): answers with ppl >= threshold have their labels zeroed
+    (they stay in the dialog as context but are not trained on).  True = keep.  NaN ppl (an answer that is only [SEP])
+    compares False with >=, so - as in the reference - it is kept."""
+    return ~(answer_ppl >= threshold)
+
+
+def nsp_rank(encoder, item, device=None) -> torch.Tensor:
+    """Discriminative ranking step of evaluate_disc.py:79-83 (BASELINE config 5): every row of ``item`` is one
+    (image, history + candidate answer) encoder input; returns softmax(nsp)[:, 0] fp32 [rows].  ``item`` uses the
+    reference's chunk keys (tokens, segments, mask, image_feat, image_loc, image_mask)."""
+    dev = torch.device(device) if device is not None else next(encoder.parameters()).device
+    out = encoder(item["tokens"].to(dev), item["image_feat"].to(dev), item["image_loc"].to(dev), token_type_ids=item["segments"].to(dev),
+                  attention_mask=item["mask"].to(dev), image_attention_mask=item["image_mask"].to(dev))
+    return torch.softmax(out[3].float(), dim=1)[:, 0]

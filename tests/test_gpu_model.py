@@ -366,3 +366,57 @@ def test_generative_ranking_shares_encoder(tiny_fp32, tiny_cfgs, tiny_sd):
         ref = lp.sum(-1).reshape(B, O)
     assert max_abs(scores, ref) < 2e-3
     assert torch.equal(scores.argsort(-1), ref.argsort(-1))
+
+
+def test_answer_perplexity_config4(tiny_fp32, tiny_cfgs, tiny_sd):
+    """Config 4 (-select_data scoring): teacher-forced ppl of given answers == generate.py:183-209 restated."""
+    from gst_visdial_b200.ranking import answer_perplexity, select_mask
+    model, _ = tiny_fp32
+    enc_cfg, dec_cfg = tiny_cfgs
+    B = 3
+    b = history_batch(enc_cfg, 0, B)
+    g = torch.Generator().manual_seed(11)
+    ans = torch.zeros(B, 18, dtype=torch.int64)
+    for i, n in enumerate((18, 7, 1)):                 # full length without [SEP], [SEP]-terminated, lone [SEP] (NaN ppl)
+        ans[i, :n] = torch.randint(104, enc_cfg.vocab_size, (n,), generator=g)
+    ans[1, 6] = 102
+    ans[2, 0] = 102
+    ppl = answer_perplexity(model, b, ans).cpu()
+    with torch.no_grad():
+        _, _, ref = R.score_answers(tiny_sd, enc_cfg, dec_cfg, b, ans)
+    ok = torch.isfinite(ref)
+    assert torch.equal(torch.isfinite(ppl), ok) and ok.tolist() == [True, True, False]
+    assert torch.allclose(ppl[ok], ref[ok], rtol=1e-3)
+    thr = float(ref[ok].mean())
+    assert torch.equal(select_mask(ppl, thr), ~(ref >= thr))
+
+
+def test_nsp_rank_config5(tiny_cfgs, tiny_sd):
+    """Config 5 (evaluate_disc.py:79-83): softmax(nsp)[:, 0] per candidate row, and the ranking it induces."""
+    from gst_visdial_b200 import weights as W
+    from gst_visdial_b200.models.visual_dialog_encoder import VisualDialogEncoder
+    from gst_visdial_b200.ranking import nsp_rank
+    enc_cfg, _ = tiny_cfgs
+    params = _params(W.TINY_ENC_CONFIG, W.TINY_DEC_CONFIG, "fp32", model="enc_only_a", mode="vd_eval_val")
+    enc = VisualDialogEncoder(params)
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in tiny_sd.items() if k.startswith("encoder.")})
+    enc.to("cuda:0").eval()
+    n_opt = 6
+    b = history_batch(enc_cfg, 0, 1)
+    g = torch.Generator().manual_seed(5)
+    tokens = b["enc_input_ids"].repeat(n_opt, 1)
+    seg = b["enc_segments"].repeat(n_opt, 1)
+    n0 = int((tokens[0] != 0).sum())
+    for o in range(n_opt):                              # each candidate appended to the text stream (dataloader_visdial_disc.py:320-323)
+        n = 3 + o
+        tokens[o, n0:n0 + n] = torch.randint(104, enc_cfg.vocab_size, (n,), generator=g)
+        tokens[o, n0 + n] = 102
+        seg[o, n0:n0 + n + 1] = 1
+    item = dict(tokens=tokens, segments=seg, mask=(tokens != 0).float(), image_feat=b["enc_image_feat"].repeat(n_opt, 1, 1),
+                image_loc=b["enc_image_loc"].repeat(n_opt, 1, 1), image_mask=b["enc_image_mask"].repeat(n_opt, 1))
+    p = nsp_rank(enc, item).cpu()
+    with torch.no_grad():
+        t, v = R.encoder(tiny_sd, enc_cfg, tokens, item["image_feat"], item["image_loc"], seg, item["mask"], item["image_mask"])
+        ref = torch.softmax(R.nsp_scores(tiny_sd, t, v), 1)[:, 0]
+    assert max_abs(p, ref) < 1e-3
+    assert torch.equal(p.argsort(descending=True), ref.argsort(descending=True))
