@@ -110,6 +110,36 @@ add_layernorm_kernel(int rows, int width, const T* __restrict__ x, int64_t ldx, 
   }
 }
 
+// Large row counts (encoder: 16 384 x 768): warps loop over rows, gamma / beta come from L1 at normalise time instead of
+// living in registers, so 32 warps per SM are resident and enough loads are in flight to approach the HBM rate.
+constexpr int kStreamWarps = 8;
+template <typename T>
+__global__ void __launch_bounds__(kStreamWarps * 32, 4)
+add_layernorm_stream_kernel(int rows, int width, const T* __restrict__ x, int64_t ldx, const T* __restrict__ res, int64_t ldr,
+                            const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ y, int64_t ldy) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * kStreamWarps;
+  for (int row = blockIdx.x * kStreamWarps + (threadIdx.x >> 5); row < rows; row += stride) {
+    float v[kMaxChunks][8];
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = (lane + 32 * c) * 8;
+      if (col < width) {
+        Vec8<T>::load(x + (int64_t)row * ldx + col, v[c]);
+        if (res != nullptr) {
+          float r[8];
+          Vec8<T>::load(res + (int64_t)row * ldr + col, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[c][j] += r[j];
+        }
+      }
+    }
+    ln_finish<T>(v, width, lane, gamma, beta, y + (int64_t)row * ldy);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kRowsPerBlock * 32)
 embed_text_kernel(int rows, int L, int width, const int64_t* __restrict__ ids, const int64_t* __restrict__ seg,
@@ -275,6 +305,16 @@ int launch_add_layernorm(int dtype, int rows, int width, const void* x, int64_t 
                          const float* gamma, const float* beta, void* y, int64_t ldy, cudaStream_t stream) {
   if (rows <= 0) return 0;
   check_width(width);
+  if (rows >= 4096) {
+    static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+    const int want = (rows + kStreamWarps - 1) / kStreamWarps, cap = sms * 4 * 2;   // two rows per warp per wave at 4 CTAs / SM
+    const int grid = want < cap ? want : cap;
+    if (dtype == kF32)
+      launch_k(add_layernorm_stream_kernel<float>, grid, kStreamWarps * 32, 0, stream, rows, width, (const float*)x, ldx, (const float*)residual, ldr, gamma, beta, (float*)y, ldy);
+    else
+      launch_k(add_layernorm_stream_kernel<bf16>, grid, kStreamWarps * 32, 0, stream, rows, width, (const bf16*)x, ldx, (const bf16*)residual, ldr, gamma, beta, (bf16*)y, ldy);
+    return 1;
+  }
   if (dtype == kF32)
     launch_k(add_layernorm_kernel<float>, grid_rows(rows), kRowsPerBlock * 32, 0, stream, rows, width, (const float*)x, ldx, (const float*)residual, ldr, gamma, beta, (float*)y, ldy);
   else

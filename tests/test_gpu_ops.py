@@ -65,7 +65,7 @@ def test_linear_simt_fp32(eng, M, N, K, act):
 
 
 @pytest.mark.parametrize("dtype,tol", [("fp32", 2e-5), ("bf16", 3e-2)])
-@pytest.mark.parametrize("rows,width", [(5, 768), (300, 1024), (37, 128), (64, 256)])
+@pytest.mark.parametrize("rows,width", [(5, 768), (300, 1024), (37, 128), (64, 256), (4100, 768)])
 def test_add_layernorm(eng, dtype, tol, rows, width):
     g = torch.Generator().manual_seed(rows + width)
     x, r = torch.randn(rows, width, generator=g) * 2, torch.randn(rows, width, generator=g)
@@ -123,6 +123,21 @@ def test_attention(eng, dtype, tol, B, heads, Lq, Lk, D, causal, neg):
         q, k, v = q.bfloat16().float(), k.bfloat16().float(), v.bfloat16().float()
     ref = _ref_attention(q, k, v, heads, mask, neg, causal)
     assert max_abs(y, ref) < tol, f"max abs {max_abs(y, ref)}"
+
+
+@pytest.mark.parametrize("heads,Lq,Lk,D,causal", [(12, 256, 256, 64, False), (8, 37, 256, 128, False), (8, 256, 37, 128, False), (12, 25, 293, 64, False),
+                                                  (12, 130, 130, 64, True)])
+def test_attention_trailing_padding_bf16(eng, heads, Lq, Lk, D, causal):
+    """History-shaped masks (valid prefix, padded tail): the tensor-core kernel skips key tiles past the last valid key."""
+    g = torch.Generator().manual_seed(Lq + 7 * Lk)
+    B, W = 4, heads * D
+    q, k, v = (torch.randn(B, L, W, generator=g) for L in (Lq, Lk, Lk))
+    lens = torch.tensor([1, min(Lk, 40), min(Lk, 130), Lk])
+    mask = (torch.arange(Lk)[None, :] < lens[:, None]).float()
+    y = eng.op_attention(q, k, v, heads, mask, neg=-10000.0, causal=causal, dtype="bf16").cpu()
+    q, k, v = q.bfloat16().float(), k.bfloat16().float(), v.bfloat16().float()
+    ref = _ref_attention(q, k, v, heads, mask, -10000.0, causal)
+    assert max_abs(y, ref) < 2e-2, f"max abs {max_abs(y, ref)}"
 
 
 def test_attention_fully_masked_row_is_finite(eng):

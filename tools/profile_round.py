@@ -21,12 +21,22 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--beams", type=int, default=5)
 ap.add_argument("--eager", action="store_true", help="launch decode steps eagerly (no CUDA graph)")
 ap.add_argument("--tiny", action="store_true")
+ap.add_argument("--hist", type=int, default=0, help="pad every history to this many tokens (0: caption only); 256 = worst case, no key tile skipped")
 a = ap.parse_args()
 enc_cfg = W.load_json_config(W.TINY_ENC_CONFIG if a.tiny else W.DEFAULT_ENC_CONFIG)
 dec_cfg = W.load_json_config(W.TINY_DEC_CONFIG if a.tiny else W.DEFAULT_DEC_CONFIG)
 eng = Engine(enc_cfg, dec_cfg, dtype="bf16", max_batch=a.batch, max_beams=a.beams, flags=_lib.GSTVD_FLAG_NO_CUDA_GRAPH if a.eager else 0)
 eng.load_state_dict(W.synthetic_state_dict(enc_cfg, dec_cfg, seed=0))
 b = S.synthetic_batch(0, a.batch, vocab_size=enc_cfg.vocab_size, v_feature_size=enc_cfg.v_feature_size)
+if a.hist:
+    g = torch.Generator().manual_seed(0)
+    ids = b["enc_input_ids"]
+    for i in range(a.batch):
+        n = int((ids[i] != 0).sum())
+        if a.hist > n:
+            ids[i, n:a.hist] = torch.randint(1000, enc_cfg.vocab_size, (a.hist - n,), generator=g)
+            ids[i, a.hist - 1] = 102
+    b["enc_att_mask"] = (ids != 0).float()
 b = {k: v.cuda() for k, v in b.items()}
 
 
