@@ -101,6 +101,7 @@ struct gstvd_ctx {
   DevBuf dh, da, db, dqkv, dctx, dtmp, dffn, dqc;      // decoder activations, rows = max(B*K, B*Ldec)
   DevBuf logits;                                      // fp32 [rows, Vpad]
   DevBuf cross_cache, self_cache;
+  DevBuf cross_len;                                   // int32 [B]: keys up to the last unmasked one (launch_cross_len)
   DevBuf labels;                                      // int64 [B*Ldec]
   DevBuf sel_val, sel_idx, logz;                      // [rows, kSelMax]
   DevBuf ban_tokens, ban_count, prefix, seq;          // sample-mode state
@@ -307,6 +308,7 @@ void alloc_workspace(gstvd_ctx* c) {
     A(c->cross_cache, (size_t)c->dec_layers * B * 2 * H * Le);
     A(c->self_cache, (size_t)c->dec_layers * 2 * B * T * K * H);
     c->labels.alloc(B * (size_t)c->Ldec_max * 8);
+    c->cross_len.alloc(B * 4);
     c->sel_val.alloc(R * kSelMax * 4); c->sel_idx.alloc(R * kSelMax * 4); c->logz.alloc(R * 4);
     c->ban_tokens.alloc(B * Lt * 4); c->ban_count.alloc(B * 4);
     c->prefix.alloc(B * (T + 1) * 4); c->seq.alloc(B * T * 4);
@@ -492,6 +494,7 @@ void do_prefill(gstvd_ctx* c, int B, int Le, const float* enc_hidden, const floa
   const int D = H / c->dec_heads;
   // one GEMM for every layer's K and V, written head-major: [layer][image][kv*heads + h][Le][D]
   X.gemm(c->fused.p, H, c->cross_kv, c->cross_cache.p, 0, B * Le, 0, false, D, Le, 2 * c->dec_heads, B);
+  c->launches += launch_cross_len(B, Le, (const float*)c->fused_mask.p, (int*)c->cross_len.p, s);
   c->cross_B = B; c->cross_Le = Le;
 }
 
@@ -527,7 +530,11 @@ void decode_step(gstvd_ctx* c, const DecodeGeom& g, const gstvd_gen_params& gp, 
     X.gemm(c->dctx.p, H, L.o, c->dtmp.p, H, M);
     X.add_ln(c->dtmp.p, c->dh.p, L.ln_att, c->da.p, M);
     X.gemm(c->da.p, H, L.cq, c->dqc.p, H, M);
-    c->launches += launch_dec_cross_attn(c->dtype, g, l, c->dqc.p, c->cross_cache.p, (const float*)c->fused_mask.p, c->dctx.p, s);
+    if (dec_cross_tma_supported(c->dtype, g))
+      c->launches += launch_dec_cross_tma(g, l, c->dqc.p, c->cross_cache.p, (const float*)c->fused_mask.p, (const int*)c->cross_len.p, c->dctx.p,
+                                          c->num_sms, s);
+    else
+      c->launches += launch_dec_cross_attn(c->dtype, g, l, c->dqc.p, c->cross_cache.p, (const float*)c->fused_mask.p, c->dctx.p, s);
     X.gemm(c->dctx.p, H, L.co, c->dtmp.p, H, M);
     X.add_ln(c->dtmp.p, c->da.p, L.ln_cross, c->db.p, M);
     X.gemm(c->db.p, H, L.f1, c->dffn.p, c->dec_F, M, 1);
@@ -780,7 +787,7 @@ void gstvd_destroy(gstvd_ctx* c) {
   for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
   DevBuf* bufs[] = {&c->mat32, &c->mat16, &c->vec32, &c->xt, &c->yt, &c->xv, &c->yv, &c->qkv_t, &c->qkv_v, &c->ctx_t, &c->ctx_v, &c->tmp_t,
                     &c->tmp_v, &c->ffn_t, &c->ffn_v, &c->feat_cast, &c->fused, &c->pool, &c->fused_mask, &c->dh, &c->da, &c->db, &c->dqkv,
-                    &c->dctx, &c->dtmp, &c->dffn, &c->dqc, &c->logits, &c->cross_cache, &c->self_cache, &c->labels, &c->sel_val, &c->sel_idx,
+                    &c->dctx, &c->dtmp, &c->dffn, &c->dqc, &c->logits, &c->cross_cache, &c->self_cache, &c->cross_len, &c->labels, &c->sel_val, &c->sel_idx,
                     &c->logz, &c->ban_tokens, &c->ban_count, &c->prefix, &c->seq, &c->beam_scores, &c->beam_tokens, &c->cur_tokens,
                     &c->beam_idx, &c->beam_done, &c->hyp_score, &c->hyp_len, &c->hyp_tokens, &c->hyp_count, &c->hyp_worst, &c->d_step, &c->d_seed};
   for (DevBuf* b : bufs) b->release();

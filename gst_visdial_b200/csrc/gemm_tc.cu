@@ -720,6 +720,17 @@ void gemm_tc_init() {
   });
 }
 
+// [groups][L][D] bf16 rows (the decoder's cross K/V cache) as a 3-D map: box = D x box_rows rows of one group, 128-byte swizzle.
+const void* tma_map_rows3(const void* ptr, int D, int L, int64_t groups, int box_rows) {
+  gemm_tc_init();
+  if (D * 2 != 128 || (reinterpret_cast<uintptr_t>(ptr) & 15) != 0) throw std::runtime_error("tma_map_rows3: rows must be 128 bytes, base 16-byte aligned");
+  MapKey key{ptr, L, D, D, box_rows, D, 2, 6, groups, 0};
+  cuuint64_t gdim[3] = {(cuuint64_t)D, (cuuint64_t)L, (cuuint64_t)groups};
+  cuuint64_t gstride[2] = {(cuuint64_t)D * 2, (cuuint64_t)L * D * 2};
+  cuuint32_t box[3] = {(cuuint32_t)D, (cuuint32_t)box_rows, 1};
+  return &cached_map(key, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
   if (a_in.M <= 0 || a_in.N <= 0) return 0;
   static const int dbg_env = [] { const char* e = getenv("GSTVD_GEMM_DBG"); return e ? atoi(e) : 0; }();

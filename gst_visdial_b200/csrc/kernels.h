@@ -113,6 +113,13 @@ int launch_dec_self_attn(int dtype, const DecodeGeom& g, int layer, const void* 
 // cross-attention of every beam row over its image's cross K/V. cross layout [layer][b][kv*heads+h][Le][D]
 int launch_dec_cross_attn(int dtype, const DecodeGeom& g, int layer, const void* q, const void* cross_cache,
                           const float* enc_mask, void* out, cudaStream_t stream);
+// TMA-streamed bf16 variant (cross_tma.cu); cross_len [B] = keys to fetch per image (launch_cross_len), may be null
+bool dec_cross_tma_supported(int dtype, const DecodeGeom& g);
+int launch_dec_cross_tma(const DecodeGeom& g, int layer, const void* q, const void* cross_cache, const float* enc_mask,
+                         const int* cross_len, void* out, int num_sms, cudaStream_t stream);
+int launch_cross_len(int B, int Le, const float* mask, int* out, cudaStream_t stream);
+// cached CUtensorMap (returned as an opaque pointer) over [groups][L][D] bf16 rows, box = D x box_rows (gemm_tc.cu)
+const void* tma_map_rows3(const void* ptr, int D, int L, int64_t groups, int box_rows);
 // in-place beam gather of the self cache over positions [0, len) ; len = *d_len if d_len else len_host
 int launch_reorder_cache(int dtype, const DecodeGeom& g, void* self_cache, const int32_t* beam_idx, const int* d_len,
                          int len_host, const uint8_t* d_skip, cudaStream_t stream);

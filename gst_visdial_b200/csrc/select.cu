@@ -9,6 +9,9 @@
 //   sample_step    : softmax + multinomial (models/visual_dialog_model.py:106-107), counter-based RNG
 //   ce_loss        : CrossEntropyLoss(ignore_index=0, reduction='none') (models/visual_dialog_decoder.py:70-77)
 //   splice         : generate.py:145-160 and :214-228
+#include <cooperative_groups.h>
+
+#include <cstdlib>
 #include <stdexcept>
 
 #include "common.cuh"
@@ -132,6 +135,282 @@ row_select_kernel(int V, const float* __restrict__ logits, int64_t ldl, int mode
       }
     }
     __syncthreads();
+  }
+}
+
+// ---- row_select, cluster version ------------------------------------------------------------------------------------
+// One thread-block CLUSTER of 4 CTAs per row: every CTA keeps 8192 consecutive vocabulary entries in registers (32 per
+// thread), the per-CTA (max, sum exp) pairs and the per-CTA sorted candidate lists are exchanged through distributed shared
+// memory.  Compared with one 1024-thread CTA per row this fills the 148 SMs evenly (1280 small CTAs instead of 320 that
+// need three waves) and shortens every block-wide reduction.  Arithmetic contract (oracle/beam.py): exp and the sum in
+// fp64, logZ rounded once to fp32, score = fp32(fp32(x - logZ) + beam_score), order (score desc, index asc).
+constexpr int kRsChunks = 4;
+constexpr int kRsThreads = 256;
+constexpr int kRsSlots = 32;
+constexpr int kRsSpan = kRsThreads * kRsSlots;
+constexpr int kRsWarps = kRsThreads / 32;
+constexpr int kRsCandCap = 128;       // candidates (elements >= tau) kept per CTA before falling back to the iterative arg-max
+
+// exp(d) for d <= 0 in fp64: k = rint(d log2 e), r = d - k ln2 (two-term Cody-Waite), degree-12 Taylor polynomial
+// (|r| <= 0.3466: truncation 1.7e-16 relative), scaled by 2^k through the exponent field.  ~17 DFMA instead of libdevice's
+// branchy ~40-instruction exp; the result is within 2 ulp, far inside what the fp32 rounding of logZ can see.
+__device__ __forceinline__ double exp_nonpos(double d) {
+  if (!(d > -700.0)) return 0.0;                     // also -inf (and NaN -> 0, never produced by finite logits)
+  const double kd = rint(d * 1.4426950408889634074);
+  double r = fma(-kd, 6.93147180369123816490e-01, d);
+  r = fma(-kd, 1.90821492927058770002e-10, r);
+  double p = 1.0 / 479001600.0;
+  p = fma(p, r, 1.0 / 39916800.0);
+  p = fma(p, r, 1.0 / 3628800.0);
+  p = fma(p, r, 1.0 / 362880.0);
+  p = fma(p, r, 1.0 / 40320.0);
+  p = fma(p, r, 1.0 / 5040.0);
+  p = fma(p, r, 1.0 / 720.0);
+  p = fma(p, r, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const int k = (int)kd;                             // >= -1010: the scale factor is a normal number
+  return p * __hiloint2double((k + 1023) << 20, 0);
+}
+
+__global__ void __cluster_dims__(kRsChunks, 1, 1) __launch_bounds__(kRsThreads)
+row_select_cluster_kernel(int V, const float* __restrict__ logits, int64_t ldl, int mode, const float* __restrict__ row_bias,
+                          float temperature, const int32_t* __restrict__ ban_tokens, const int32_t* __restrict__ ban_count,
+                          int ban_stride, int nsel, float* __restrict__ sel_val, int32_t* __restrict__ sel_idx, float* __restrict__ logz) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float s_f[kRsWarps];
+  __shared__ double s_d[kRsWarps];
+  __shared__ int s_i[kRsWarps];
+  __shared__ int s_bcast_i;
+  __shared__ float s_lz;
+  __shared__ double s_part[2];                       // this CTA's (max, sum exp(x - max)); read by the peers
+  __shared__ float s_cv[kSelMax];                    // this CTA's candidates, best first; read by rank 0
+  __shared__ int s_ci[kSelMax];
+  __shared__ float s_tmax[kRsThreads];
+  __shared__ float s_candv[kRsCandCap];
+  __shared__ int s_candi[kRsCandCap];
+  __shared__ int s_cnt;
+  __shared__ float s_tau;
+  __shared__ float s_allv[kRsChunks * kSelMax];
+  __shared__ int s_alli[kRsChunks * kSelMax];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int chunk = (int)cluster.block_rank();
+  const int row = blockIdx.x / kRsChunks, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int base = chunk * kRsSpan;
+  const float* __restrict__ x = logits + (int64_t)row * ldl;
+  float v[kRsSlots];
+#pragma unroll
+  for (int s = 0; s < kRsSlots; ++s) {
+    const int idx = base + tid + s * kRsThreads;
+    v[s] = (idx < V) ? x[idx] : -INFINITY;
+  }
+  float lz = 0.f;
+  const bool need_lz = (mode == 0 || logz != nullptr);
+  if (need_lz) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < kRsSlots; ++s) m = fmaxf(m, v[s]);
+    m = warp_max(m);
+    if (lane == 0) s_f[warp] = m;
+    __syncthreads();
+    m = s_f[lane & (kRsWarps - 1)];
+    m = warp_max(m);
+    __syncthreads();
+    double acc = 0.0;
+    if (m > -INFINITY) {
+#pragma unroll
+      for (int s = 0; s < kRsSlots; ++s)
+        if (base + tid + s * kRsThreads < V) acc += exp_nonpos((double)v[s] - (double)m);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_d[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < kRsWarps; ++w) t += s_d[w];
+      s_part[0] = (double)m;
+      s_part[1] = t;
+    }
+  }
+  cluster.sync();                                    // (also orders the plain shared-memory writes above)
+  if (need_lz) {
+    if (tid == 0) {
+      double pm[kRsChunks], ps[kRsChunks], gm = -INFINITY;
+      for (int r = 0; r < kRsChunks; ++r) {
+        const double* rp = cluster.map_shared_rank(s_part, r);
+        pm[r] = rp[0]; ps[r] = rp[1];
+        gm = fmax(gm, pm[r]);
+      }
+      double tot = 0.0;
+      for (int r = 0; r < kRsChunks; ++r) tot += ps[r] * exp_nonpos(pm[r] - gm);
+      s_lz = (float)(gm + log(tot));
+    }
+    __syncthreads();
+    lz = s_lz;
+    if (logz != nullptr && tid == 0 && chunk == 0) logz[row] = lz;
+  }
+  if (mode == 0) {
+    const float bias = row_bias ? row_bias[row] : 0.f;
+#pragma unroll
+    for (int s = 0; s < kRsSlots; ++s)
+      if (base + tid + s * kRsThreads < V) v[s] = __fadd_rn(__fsub_rn(v[s], lz), bias);
+  } else {
+#pragma unroll
+    for (int s = 0; s < kRsSlots; ++s)
+      if (base + tid + s * kRsThreads < V) v[s] = __fdiv_rn(v[s], temperature);
+    const int nb = ban_count ? ban_count[row] : 0;
+    for (int j = 0; j < nb; ++j) {
+      const int w = ban_tokens[(int64_t)row * ban_stride + j] - base;
+      if (w >= 0 && w < kRsSpan && (w % kRsThreads) == tid) {
+        const int slot = w / kRsThreads;
+#pragma unroll
+        for (int s = 0; s < kRsSlots; ++s)
+          if (s == slot) v[s] = -INFINITY;
+      }
+    }
+  }
+  // ---- this CTA's nsel best ----
+  // Filter first: the nsel-th largest of the 256 per-thread maxima (tau) is a lower bound of the CTA's nsel-th largest
+  // element, so only elements >= tau can be selected - typically nsel..2*nsel of the 8192.  They are collected in shared
+  // memory and one warp orders them by (value desc, index asc).  ~3 instructions per element instead of ~60 for a
+  // block-wide iterative arg-max; the iterative path remains as the fallback when the candidate list overflows (mass ties).
+  float tv = -INFINITY;
+#pragma unroll
+  for (int s = 0; s < kRsSlots; ++s) tv = fmaxf(tv, v[s]);           // invalid / banned slots hold -inf
+  s_tmax[tid] = tv;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  if (warp == 0) {
+    float l[kRsThreads / 32];
+#pragma unroll
+    for (int i = 0; i < kRsThreads / 32; ++i) l[i] = s_tmax[lane + 32 * i];
+    float tau = -INFINITY;
+    for (int r = 0; r < nsel; ++r) {
+      float lm = l[0];
+#pragma unroll
+      for (int i = 1; i < kRsThreads / 32; ++i) lm = fmaxf(lm, l[i]);
+      const float wm = warp_max(lm);
+      tau = wm;
+      if (wm == -INFINITY) break;                                     // fewer than nsel finite maxima: everything finite is a candidate
+      const unsigned ball = __ballot_sync(0xffffffffu, lm == wm);
+      if (lane == __ffs(ball) - 1) {                                  // retire ONE instance of the maximum
+        bool done = false;
+#pragma unroll
+        for (int i = 0; i < kRsThreads / 32; ++i)
+          if (!done && l[i] == wm) { l[i] = -INFINITY; done = true; }
+      }
+    }
+    if (lane == 0) s_tau = tau;
+  }
+  __syncthreads();
+  {
+    const float tau = s_tau;
+#pragma unroll
+    for (int s = 0; s < kRsSlots; ++s) {
+      if (v[s] >= tau && v[s] > -INFINITY) {
+        const int pos = atomicAdd(&s_cnt, 1);
+        if (pos < kRsCandCap) { s_candv[pos] = v[s]; s_candi[pos] = base + tid + s * kRsThreads; }
+      }
+    }
+  }
+  __syncthreads();
+  const int ncand = s_cnt;
+  if (ncand <= kRsCandCap) {
+    if (warp == 0) {
+      float cv4[kRsCandCap / 32]; int ci4[kRsCandCap / 32];
+#pragma unroll
+      for (int i = 0; i < kRsCandCap / 32; ++i) {
+        const int j = lane + 32 * i;
+        cv4[i] = j < ncand ? s_candv[j] : -INFINITY;
+        ci4[i] = j < ncand ? s_candi[j] : 0x7fffffff;
+      }
+      for (int r = 0; r < nsel; ++r) {
+        float cv = -INFINITY; int ci = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < kRsCandCap / 32; ++i)
+          if (ci4[i] != 0x7fffffff && better(cv4[i], ci4[i], cv, ci)) { cv = cv4[i]; ci = ci4[i]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
+          if (better(ov, oi, cv, ci)) { cv = ov; ci = oi; }
+        }
+        if (lane == 0) { s_cv[r] = cv; s_ci[r] = ci; }
+#pragma unroll
+        for (int i = 0; i < kRsCandCap / 32; ++i)
+          if (ci4[i] == ci) { cv4[i] = -INFINITY; ci4[i] = 0x7fffffff; }
+      }
+    }
+  } else {
+    // fallback: iterative block-wide arg-max (ties towards the lower index); only the previous winner's owner rescans
+    float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+    for (int s = 0; s < kRsSlots; ++s) {
+      const int idx = base + tid + s * kRsThreads;
+      if (idx < V && v[s] > -INFINITY && better(v[s], idx, bv, bi)) { bv = v[s]; bi = idx; }
+    }
+    for (int r = 0; r < nsel; ++r) {
+      float cv = bv; int ci = bi;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
+        if (better(ov, oi, cv, ci)) { cv = ov; ci = oi; }
+      }
+      if (lane == 0) { s_f[warp] = cv; s_i[warp] = ci; }
+      __syncthreads();
+      if (warp == 0) {
+        cv = s_f[lane & (kRsWarps - 1)]; ci = s_i[lane & (kRsWarps - 1)];
+#pragma unroll
+        for (int o = kRsWarps / 2; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
+          if (better(ov, oi, cv, ci)) { cv = ov; ci = oi; }
+        }
+        if (lane == 0) { s_bcast_i = ci; s_cv[r] = cv; s_ci[r] = ci; }
+      }
+      __syncthreads();
+      const int wi = s_bcast_i;
+      if (wi != 0x7fffffff && ((wi - base) % kRsThreads) == tid) {
+        const int slot = (wi - base) / kRsThreads;
+        bv = -INFINITY; bi = 0x7fffffff;
+#pragma unroll
+        for (int s = 0; s < kRsSlots; ++s) {
+          if (s == slot) v[s] = -INFINITY;
+          const int idx = base + tid + s * kRsThreads;
+          if (idx < V && v[s] > -INFINITY && better(v[s], idx, bv, bi)) { bv = v[s]; bi = idx; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  cluster.sync();                                    // every CTA's candidate list is complete
+  if (chunk == 0 && tid < kRsChunks * nsel) {
+    const int r = tid / nsel, j = tid - r * nsel;
+    s_allv[tid] = cluster.map_shared_rank(s_cv, r)[j];
+    s_alli[tid] = cluster.map_shared_rank(s_ci, r)[j];
+  }
+  cluster.sync();                                    // the peers may exit: rank 0 holds a copy of their lists
+  if (chunk == 0 && tid == 0) {
+    int head[kRsChunks] = {0, 0, 0, 0};
+    for (int r = 0; r < nsel; ++r) {
+      float cv = -INFINITY; int ci = 0x7fffffff, from = -1;
+      for (int q = 0; q < kRsChunks; ++q) {
+        if (head[q] < nsel) {
+          const float ov = s_allv[q * nsel + head[q]];
+          const int oi = s_alli[q * nsel + head[q]];
+          if (oi != 0x7fffffff && better(ov, oi, cv, ci)) { cv = ov; ci = oi; from = q; }
+        }
+      }
+      if (from >= 0) ++head[from];
+      sel_val[(int64_t)row * nsel + r] = cv;
+      sel_idx[(int64_t)row * nsel + r] = (ci == 0x7fffffff) ? 0 : ci;
+    }
   }
 }
 
@@ -474,8 +753,13 @@ int launch_row_select(int rows, int V, const float* logits, int64_t ldl, int mod
   if (rows <= 0) return 0;
   if (V > kSelThreads * kSlots) throw std::runtime_error("row_select: vocab > 32768");
   if (nsel > kSelMax || nsel < 1) throw std::runtime_error("row_select: nsel out of range");
-  launch_k(row_select_kernel, dim3(rows), dim3(kSelThreads), 0, stream, V, logits, ldl, mode, row_bias, temperature, ban_tokens, ban_count,
-                                                      ban_stride, nsel, sel_val, sel_idx, logz);
+  static const bool v1 = getenv("GSTVD_ROW_SELECT_V1") != nullptr;      // A/B aid: the single-CTA-per-row kernel
+  if (v1)
+    launch_k(row_select_kernel, dim3(rows), dim3(kSelThreads), 0, stream, V, logits, ldl, mode, row_bias, temperature, ban_tokens, ban_count,
+             ban_stride, nsel, sel_val, sel_idx, logz);
+  else
+    launch_k(row_select_cluster_kernel, dim3(rows * kRsChunks), dim3(kRsThreads), 0, stream, V, logits, ldl, mode, row_bias, temperature,
+             ban_tokens, ban_count, ban_stride, nsel, sel_val, sel_idx, logz);
   return 1;
 }
 

@@ -151,6 +151,29 @@ def test_attention_fully_masked_row_is_finite(eng):
     assert torch.isfinite(y).all() and max_abs(y, ref) < 5e-3
 
 
+def test_beam_step_mass_ties_vs_oracle(eng, full_cfgs):
+    """Hundreds of exactly equal top logits (and a constant row): the candidate filter of row_select overflows and the
+    iterative arg-max fallback must still order by (score desc, index asc) like the oracle."""
+    V, T, B, K = full_cfgs[1].vocab_size, 4, 2, 3
+    g = torch.Generator().manual_seed(77)
+    st = OB.BeamState(B, K, V, T)
+    eng.op_beam_begin(B, K, T)
+    for t in range(T):
+        logits = torch.randn(B * K, V, generator=g)
+        if t == 0:
+            logits[:] = 0.25                                  # every token ties
+        if t == 1:
+            logits[:, 9000:9400] = 7.0                        # 400 tied maxima inside one 8192-entry chunk
+        if t == 2:
+            logits[:, 5::97] = 6.5                            # ~315 tied maxima spread over all chunks
+        bi, bt, bs = st.step(logits)
+        gi, gt, gs = eng.op_beam_step(logits)
+        assert torch.equal(gi.cpu().long(), bi) and torch.equal(gt.cpu().long(), bt) and torch.equal(gs.cpu(), bs), f"step {t}"
+    seq, _ = st.finalize()
+    gseq, _ = eng.op_beam_end(T)
+    assert torch.equal(gseq.cpu(), seq)
+
+
 @pytest.mark.parametrize("B,K", [(3, 5), (2, 1), (4, 2)])
 def test_beam_step_bit_exact_vs_oracle(eng, full_cfgs, B, K):
     """Identical fp32 logits into the CUDA beam kernels and oracle/beam.py: parents, tokens, scores and the final
