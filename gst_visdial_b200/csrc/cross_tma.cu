@@ -75,9 +75,21 @@ dec_cross_tma_kernel(const __grid_constant__ CUtensorMap tm, DecodeGeom g, int l
     if (lane < nb) tma_load_3d(buf + lane * kXtBoxBytes, &tm, 0, lane * kXtRows, z, bar);
   };
   // additive mask row of image b in the log2 domain; -inf past the encoder length
-  auto fill_madd = [&](float* dst, int b, int nk16) {
-    for (int j = tid; j < nk16; j += kXtThreads)
-      dst[j] = (j < g.Le) ? (1.0f - (enc_mask ? enc_mask[(int64_t)b * g.Le + j] : 1.f)) * (-1e9f * kLog2e) : -INFINITY;
+  // (two entries per thread: 2 x 256 >= 304; loaded early into registers, stored once the previous reader is done)
+  float mk[2];
+  auto load_mask = [&](int b) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int j = tid + i * kXtThreads;
+      mk[i] = (j < g.Le) ? (1.0f - (enc_mask ? enc_mask[(int64_t)b * g.Le + j] : 1.f)) * (-1e9f * kLog2e) : -INFINITY;
+    }
+  };
+  auto store_mask = [&](float* dst) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int j = tid + i * kXtThreads;
+      if (j < kXtLeP) dst[j] = mk[i];
+    }
   };
   // query fragments (A operand: row = beam, natural head-dim order) straight from global
   uint32_t qa0[4], qa2[4];
@@ -100,7 +112,8 @@ dec_cross_tma_kernel(const __grid_constant__ CUtensorMap tm, DecodeGeom g, int l
     issue(first, 0, k_buf, bar_k);                          // cross K/V, cross_len and the mask date from the prefill: safe before the wait
     issue(first, 1, v_buf, bar_v);
   }
-  fill_madd(madd, first / g.heads, ((keys_of(first / g.heads) + 15) >> 4) << 4);
+  load_mask(first / g.heads);
+  store_mask(madd);
   pdl_wait();                                               // the query projection of this step is complete
   load_q(first);
 
@@ -116,6 +129,7 @@ dec_cross_tma_kernel(const __grid_constant__ CUtensorMap tm, DecodeGeom g, int l
     uint32_t a_q0[4], a_q2[4];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) { a_q0[kk] = qa0[kk]; a_q2[kk] = qa2[kk]; }
+    if (next < items) load_mask(next / g.heads);            // consumed after the scores: the loads have landed by then
     __syncthreads();                                        // mask row visible; the previous item's partial sums have been read
     mbar_wait(bar_k, phase);
     // ---- scores: 16-key groups strided over the warps ----
@@ -143,8 +157,7 @@ dec_cross_tma_kernel(const __grid_constant__ CUtensorMap tm, DecodeGeom g, int l
     if (next < items) {
       if (warp == 0) issue(next, 0, k_buf, bar_k);
       load_q(next);                                         // in flight during the softmax / context phases
-      const int nb2 = next / g.heads;
-      fill_madd(madd + (cur ^ 1) * kXtLeP, nb2, ((keys_of(nb2) + 15) >> 4) << 4);
+      store_mask(madd + (cur ^ 1) * kXtLeP);
     }
     // ---- softmax over the fetched keys, one warp per beam; probabilities as bf16 ----
     for (int k = warp; k < g.K; k += kXtWarps) {

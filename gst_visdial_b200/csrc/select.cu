@@ -140,43 +140,43 @@ row_select_kernel(int V, const float* __restrict__ logits, int64_t ldl, int mode
 
 // ---- row_select, cluster version ------------------------------------------------------------------------------------
 // One thread-block CLUSTER of 4 CTAs per row: every CTA keeps 8192 consecutive vocabulary entries in registers (32 per
-// thread), the per-CTA (max, sum exp) pairs and the per-CTA sorted candidate lists are exchanged through distributed shared
-// memory.  Compared with one 1024-thread CTA per row this fills the 148 SMs evenly (1280 small CTAs instead of 320 that
-// need three waves) and shortens every block-wide reduction.  Arithmetic contract (oracle/beam.py): exp and the sum in
-// fp64, logZ rounded once to fp32, score = fp32(fp32(x - logZ) + beam_score), order (score desc, index asc).
+// thread); the per-CTA (max, sum exp) pairs and candidate lists are exchanged through distributed shared memory.
+// Compared with one 1024-thread CTA per row this fills the 148 SMs evenly (1280 small CTAs instead of 320 that need three
+// waves).  No warp-serial loops: the selection threshold and every ordering step are RANK computations (each element
+// counts the elements that beat it), which are independent instructions instead of dependent shuffle chains.
+// Arithmetic contract (oracle/beam.py): exp and the sum in fp64, logZ rounded once to fp32,
+// score = fp32(fp32(x - logZ) + beam_score), order (score desc, index asc).
 constexpr int kRsChunks = 4;
 constexpr int kRsThreads = 256;
 constexpr int kRsSlots = 32;
 constexpr int kRsSpan = kRsThreads * kRsSlots;
 constexpr int kRsWarps = kRsThreads / 32;
+constexpr int kRsGroups = 16;         // half-warp groups whose maxima bound the nsel-th largest element (nsel <= 16)
 constexpr int kRsCandCap = 128;       // candidates (elements >= tau) kept per CTA before falling back to the iterative arg-max
+constexpr int kFill = 0x7fffff00;     // candidate indices >= kFill are fillers ("no candidate"), distinct so that ranks are unique
+static_assert(kSelMax <= kRsGroups, "the threshold needs at least nsel groups");
+
+// Taylor coefficients 1/12! .. 1/0! in constant memory: DFMA takes them as constant-bank operands (64-bit literals would
+// be rebuilt with two UMOVs per use).
+__constant__ double kExpPoly[13] = {1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0,
+                                    1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
+__constant__ double kExpRed[3] = {1.4426950408889634074, 6.93147180369123816490e-01, 1.90821492927058770002e-10};
 
 // exp(d) for d <= 0 in fp64: k = rint(d log2 e), r = d - k ln2 (two-term Cody-Waite), degree-12 Taylor polynomial
-// (|r| <= 0.3466: truncation 1.7e-16 relative), scaled by 2^k through the exponent field.  ~17 DFMA instead of libdevice's
-// branchy ~40-instruction exp; the result is within 2 ulp, far inside what the fp32 rounding of logZ can see.
+// (|r| <= 0.3466: truncation 1.7e-16 relative), scaled by 2^k through the exponent field.  Within 2 ulp - far inside what
+// the fp32 rounding of logZ can see - at ~17 DFMA instead of libdevice's branchy exp.
 __device__ __forceinline__ double exp_nonpos(double d) {
-  if (!(d > -700.0)) return 0.0;                     // also -inf (and NaN -> 0, never produced by finite logits)
-  const double kd = rint(d * 1.4426950408889634074);
-  double r = fma(-kd, 6.93147180369123816490e-01, d);
-  r = fma(-kd, 1.90821492927058770002e-10, r);
-  double p = 1.0 / 479001600.0;
-  p = fma(p, r, 1.0 / 39916800.0);
-  p = fma(p, r, 1.0 / 3628800.0);
-  p = fma(p, r, 1.0 / 362880.0);
-  p = fma(p, r, 1.0 / 40320.0);
-  p = fma(p, r, 1.0 / 5040.0);
-  p = fma(p, r, 1.0 / 720.0);
-  p = fma(p, r, 1.0 / 120.0);
-  p = fma(p, r, 1.0 / 24.0);
-  p = fma(p, r, 1.0 / 6.0);
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  const int k = (int)kd;                             // >= -1010: the scale factor is a normal number
-  return p * __hiloint2double((k + 1023) << 20, 0);
+  d = fmax(d, -700.0);                               // exp(-700) ~ 1e-304: contributes nothing; keeps 2^k a normal number
+  const double kd = rint(d * kExpRed[0]);
+  double r = fma(-kd, kExpRed[1], d);
+  r = fma(-kd, kExpRed[2], r);
+  double p = kExpPoly[0];
+#pragma unroll
+  for (int i = 1; i < 13; ++i) p = fma(p, r, kExpPoly[i]);
+  return p * __hiloint2double(((int)kd + 1023) << 20, 0);
 }
 
-__global__ void __cluster_dims__(kRsChunks, 1, 1) __launch_bounds__(kRsThreads)
+__global__ void __cluster_dims__(kRsChunks, 1, 1) __launch_bounds__(kRsThreads, 3)
 row_select_cluster_kernel(int V, const float* __restrict__ logits, int64_t ldl, int mode, const float* __restrict__ row_bias,
                           float temperature, const int32_t* __restrict__ ban_tokens, const int32_t* __restrict__ ban_count,
                           int ban_stride, int nsel, float* __restrict__ sel_val, int32_t* __restrict__ sel_idx, float* __restrict__ logz) {
@@ -188,14 +188,13 @@ row_select_cluster_kernel(int V, const float* __restrict__ logits, int64_t ldl, 
   __shared__ int s_bcast_i;
   __shared__ float s_lz;
   __shared__ double s_part[2];                       // this CTA's (max, sum exp(x - max)); read by the peers
-  __shared__ float s_cv[kSelMax];                    // this CTA's candidates, best first; read by rank 0
-  __shared__ int s_ci[kSelMax];
-  __shared__ float s_tmax[kRsThreads];
+  __shared__ float s_g[kRsGroups];                   // half-warp maxima
   __shared__ float s_candv[kRsCandCap];
   __shared__ int s_candi[kRsCandCap];
   __shared__ int s_cnt;
-  __shared__ float s_tau;
-  __shared__ float s_allv[kRsChunks * kSelMax];
+  __shared__ float s_cv[kSelMax];                    // this CTA's nsel best, best first
+  __shared__ int s_ci[kSelMax];
+  __shared__ float s_allv[kRsChunks * kSelMax];      // rank 0: the lists of all four CTAs (written by the peers)
   __shared__ int s_alli[kRsChunks * kSelMax];
   pdl_wait();
   pdl_launch_dependents();
@@ -209,6 +208,7 @@ row_select_cluster_kernel(int V, const float* __restrict__ logits, int64_t ldl, 
     const int idx = base + tid + s * kRsThreads;
     v[s] = (idx < V) ? x[idx] : -INFINITY;
   }
+  if (tid == 0) s_cnt = 0;
   float lz = 0.f;
   const bool need_lz = (mode == 0 || logz != nullptr);
   if (need_lz) {
@@ -220,35 +220,38 @@ row_select_cluster_kernel(int V, const float* __restrict__ logits, int64_t ldl, 
     __syncthreads();
     m = s_f[lane & (kRsWarps - 1)];
     m = warp_max(m);
-    __syncthreads();
     double acc = 0.0;
     if (m > -INFINITY) {
+      const double md = (double)m;
 #pragma unroll
       for (int s = 0; s < kRsSlots; ++s)
-        if (base + tid + s * kRsThreads < V) acc += exp_nonpos((double)v[s] - (double)m);
+        if (base + tid + s * kRsThreads < V) acc += exp_nonpos((double)v[s] - md);
     }
     acc = warp_sum(acc);
     if (lane == 0) s_d[warp] = acc;
     __syncthreads();
     if (tid == 0) {
       double t = 0.0;
+#pragma unroll
       for (int w = 0; w < kRsWarps; ++w) t += s_d[w];
       s_part[0] = (double)m;
       s_part[1] = t;
     }
-  }
-  cluster.sync();                                    // (also orders the plain shared-memory writes above)
-  if (need_lz) {
-    if (tid == 0) {
-      double pm[kRsChunks], ps[kRsChunks], gm = -INFINITY;
-      for (int r = 0; r < kRsChunks; ++r) {
-        const double* rp = cluster.map_shared_rank(s_part, r);
-        pm[r] = rp[0]; ps[r] = rp[1];
-        gm = fmax(gm, pm[r]);
+    cluster.sync();                                  // every CTA's (max, sum) is published
+    if (warp == 0) {
+      double pm = -INFINITY, ps = 0.0;
+      if (lane < kRsChunks) {
+        const double* rp = cluster.map_shared_rank(s_part, lane);
+        pm = rp[0]; ps = rp[1];
       }
-      double tot = 0.0;
-      for (int r = 0; r < kRsChunks; ++r) tot += ps[r] * exp_nonpos(pm[r] - gm);
-      s_lz = (float)(gm + log(tot));
+      double gm = pm;
+#pragma unroll
+      for (int o = 2; o > 0; o >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+      double term = (lane < kRsChunks && pm > -INFINITY) ? ps * exp_nonpos(pm - gm) : 0.0;
+      // fixed order 0+1, 2+3, then the pair sums: identical in all four CTAs
+      term += __shfl_xor_sync(0xffffffffu, term, 1);
+      term += __shfl_xor_sync(0xffffffffu, term, 2);
+      if (lane == 0) s_lz = (float)(gm + log(term));
     }
     __syncthreads();
     lz = s_lz;
@@ -275,76 +278,47 @@ row_select_cluster_kernel(int V, const float* __restrict__ logits, int64_t ldl, 
     }
   }
   // ---- this CTA's nsel best ----
-  // Filter first: the nsel-th largest of the 256 per-thread maxima (tau) is a lower bound of the CTA's nsel-th largest
-  // element, so only elements >= tau can be selected - typically nsel..2*nsel of the 8192.  They are collected in shared
-  // memory and one warp orders them by (value desc, index asc).  ~3 instructions per element instead of ~60 for a
-  // block-wide iterative arg-max; the iterative path remains as the fallback when the candidate list overflows (mass ties).
+  // Filter first.  The 16 half-warp maxima are 16 distinct elements, so their nsel-th largest (tau) is a lower bound of
+  // the CTA's nsel-th largest element and only elements >= tau can be selected - ~16 of the 8192 on average.  They are
+  // collected in shared memory and ordered by rank.  The iterative block-wide arg-max remains as the fallback when the
+  // candidate list overflows (mass ties).
   float tv = -INFINITY;
 #pragma unroll
   for (int s = 0; s < kRsSlots; ++s) tv = fmaxf(tv, v[s]);           // invalid / banned slots hold -inf
-  s_tmax[tid] = tv;
-  if (tid == 0) s_cnt = 0;
-  __syncthreads();
-  if (warp == 0) {
-    float l[kRsThreads / 32];
 #pragma unroll
-    for (int i = 0; i < kRsThreads / 32; ++i) l[i] = s_tmax[lane + 32 * i];
-    float tau = -INFINITY;
-    for (int r = 0; r < nsel; ++r) {
-      float lm = l[0];
-#pragma unroll
-      for (int i = 1; i < kRsThreads / 32; ++i) lm = fmaxf(lm, l[i]);
-      const float wm = warp_max(lm);
-      tau = wm;
-      if (wm == -INFINITY) break;                                     // fewer than nsel finite maxima: everything finite is a candidate
-      const unsigned ball = __ballot_sync(0xffffffffu, lm == wm);
-      if (lane == __ffs(ball) - 1) {                                  // retire ONE instance of the maximum
-        bool done = false;
-#pragma unroll
-        for (int i = 0; i < kRsThreads / 32; ++i)
-          if (!done && l[i] == wm) { l[i] = -INFINITY; done = true; }
-      }
-    }
-    if (lane == 0) s_tau = tau;
-  }
-  __syncthreads();
+  for (int o = 8; o > 0; o >>= 1) tv = fmaxf(tv, __shfl_xor_sync(0xffffffffu, tv, o));
+  if ((lane & 15) == 0) s_g[tid >> 4] = tv;
+  __syncthreads();                                                     // (also publishes s_cnt = 0)
+  float tau;
   {
-    const float tau = s_tau;
+    // every warp ranks the 16 maxima redundantly (lanes 16..31 mirror 0..15): no second barrier
+    const float mine = s_g[lane & 15];
+    int rank = 0;
 #pragma unroll
-    for (int s = 0; s < kRsSlots; ++s) {
-      if (v[s] >= tau && v[s] > -INFINITY) {
-        const int pos = atomicAdd(&s_cnt, 1);
-        if (pos < kRsCandCap) { s_candv[pos] = v[s]; s_candi[pos] = base + tid + s * kRsThreads; }
-      }
+    for (int j = 0; j < kRsGroups; ++j) {
+      const float other = __shfl_sync(0xffffffffu, mine, j);
+      rank += (other > mine || (other == mine && j < (lane & 15))) ? 1 : 0;
+    }
+    const unsigned pick = __ballot_sync(0xffffffffu, rank == nsel - 1);
+    tau = __shfl_sync(0xffffffffu, mine, __ffs(pick) - 1);
+  }
+#pragma unroll
+  for (int s = 0; s < kRsSlots; ++s) {
+    if (v[s] >= tau && v[s] > -INFINITY) {
+      const int pos = atomicAdd(&s_cnt, 1);
+      if (pos < kRsCandCap) { s_candv[pos] = v[s]; s_candi[pos] = base + tid + s * kRsThreads; }
     }
   }
   __syncthreads();
   const int ncand = s_cnt;
   if (ncand <= kRsCandCap) {
-    if (warp == 0) {
-      float cv4[kRsCandCap / 32]; int ci4[kRsCandCap / 32];
-#pragma unroll
-      for (int i = 0; i < kRsCandCap / 32; ++i) {
-        const int j = lane + 32 * i;
-        cv4[i] = j < ncand ? s_candv[j] : -INFINITY;
-        ci4[i] = j < ncand ? s_candi[j] : 0x7fffffff;
-      }
-      for (int r = 0; r < nsel; ++r) {
-        float cv = -INFINITY; int ci = 0x7fffffff;
-#pragma unroll
-        for (int i = 0; i < kRsCandCap / 32; ++i)
-          if (ci4[i] != 0x7fffffff && better(cv4[i], ci4[i], cv, ci)) { cv = cv4[i]; ci = ci4[i]; }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, cv, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
-          if (better(ov, oi, cv, ci)) { cv = ov; ci = oi; }
-        }
-        if (lane == 0) { s_cv[r] = cv; s_ci[r] = ci; }
-#pragma unroll
-        for (int i = 0; i < kRsCandCap / 32; ++i)
-          if (ci4[i] == ci) { cv4[i] = -INFINITY; ci4[i] = 0x7fffffff; }
-      }
+    if (tid < nsel && tid >= ncand) { s_cv[tid] = -INFINITY; s_ci[tid] = kFill + tid; }
+    if (tid < ncand) {
+      const float mv = s_candv[tid];
+      const int mi = s_candi[tid];
+      int rank = 0;
+      for (int j = 0; j < ncand; ++j) rank += better(s_candv[j], s_candi[j], mv, mi) ? 1 : 0;
+      if (rank < nsel) { s_cv[rank] = mv; s_ci[rank] = mi; }
     }
   } else {
     // fallback: iterative block-wide arg-max (ties towards the lower index); only the previous winner's owner rescans
@@ -372,7 +346,7 @@ row_select_cluster_kernel(int V, const float* __restrict__ logits, int64_t ldl, 
           const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
           if (better(ov, oi, cv, ci)) { cv = ov; ci = oi; }
         }
-        if (lane == 0) { s_bcast_i = ci; s_cv[r] = cv; s_ci[r] = ci; }
+        if (lane == 0) { s_bcast_i = ci; s_cv[r] = cv; s_ci[r] = (ci == 0x7fffffff) ? kFill + r : ci; }
       }
       __syncthreads();
       const int wi = s_bcast_i;
@@ -389,27 +363,22 @@ row_select_cluster_kernel(int V, const float* __restrict__ logits, int64_t ldl, 
       __syncthreads();
     }
   }
-  cluster.sync();                                    // every CTA's candidate list is complete
-  if (chunk == 0 && tid < kRsChunks * nsel) {
-    const int r = tid / nsel, j = tid - r * nsel;
-    s_allv[tid] = cluster.map_shared_rank(s_cv, r)[j];
-    s_alli[tid] = cluster.map_shared_rank(s_ci, r)[j];
+  __syncthreads();
+  // push this CTA's list into rank 0's table; fillers become distinct per (chunk, position)
+  if (tid < nsel) {
+    const int ci = s_ci[tid];
+    cluster.map_shared_rank(s_allv, 0)[chunk * nsel + tid] = s_cv[tid];
+    cluster.map_shared_rank(s_alli, 0)[chunk * nsel + tid] = ci >= kFill ? kFill + chunk * kSelMax + tid : ci;
   }
-  cluster.sync();                                    // the peers may exit: rank 0 holds a copy of their lists
-  if (chunk == 0 && tid == 0) {
-    int head[kRsChunks] = {0, 0, 0, 0};
-    for (int r = 0; r < nsel; ++r) {
-      float cv = -INFINITY; int ci = 0x7fffffff, from = -1;
-      for (int q = 0; q < kRsChunks; ++q) {
-        if (head[q] < nsel) {
-          const float ov = s_allv[q * nsel + head[q]];
-          const int oi = s_alli[q * nsel + head[q]];
-          if (oi != 0x7fffffff && better(ov, oi, cv, ci)) { cv = ov; ci = oi; from = q; }
-        }
-      }
-      if (from >= 0) ++head[from];
-      sel_val[(int64_t)row * nsel + r] = cv;
-      sel_idx[(int64_t)row * nsel + r] = (ci == 0x7fffffff) ? 0 : ci;
+  cluster.sync();                                    // the table is complete; the peers are done
+  if (chunk == 0 && tid < kRsChunks * nsel) {
+    const float mv = s_allv[tid];
+    const int mi = s_alli[tid];
+    int rank = 0;
+    for (int j = 0; j < kRsChunks * nsel; ++j) rank += better(s_allv[j], s_alli[j], mv, mi) ? 1 : 0;
+    if (rank < nsel) {
+      sel_val[(int64_t)row * nsel + rank] = mv;
+      sel_idx[(int64_t)row * nsel + rank] = mi >= kFill ? 0 : mi;
     }
   }
 }
