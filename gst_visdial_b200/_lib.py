@@ -20,6 +20,7 @@ GSTVD_FLAG_NO_CUDA_GRAPH = 1
 GSTVD_FLAG_DEBUG_SIMT_GEMM = 2
 GSTVD_FLAG_GENERIC_ATTENTION = 4
 GSTVD_FLAG_NO_PDL = 8
+GSTVD_FLAG_SHARED_SM_GEMM = 16
 GSTVD_MAX_TOP_K = 16
 
 STATUS_NAMES = {0: "OK", -1: "INVALID", -2: "CUDA", -3: "UNSUPPORTED", -4: "STATE"}

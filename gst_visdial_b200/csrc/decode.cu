@@ -39,8 +39,9 @@ template <> struct Raw16<float> {
 // Self-attention of one new position per (beam row, head) over the persistent cache (one warp per (row, head)).
 // Scores: lane t owns cached position t and reads its whole key row (16-byte loads, all issued back to back) against the
 // query held in shared memory - no serial chain of load + warp-reduction per position; the new position's score is one
-// warp reduction.  P*V: lanes split the head dimension, the value rows of 6 positions are in flight at a time.
-template <typename T>
+// warp reduction.  P*V: lanes split the head dimension; the value rows of the first 16 positions are requested BEFORE the
+// scores are computed (they do not depend on them), so key and value loads share one memory round trip.
+template <typename T, int ND>
 __global__ void __launch_bounds__(128)
 dec_self_attn_kernel(DecodeGeom g, int layer, const T* __restrict__ qkv, T* __restrict__ cache, const int* __restrict__ d_step,
                      T* __restrict__ out) {
@@ -55,7 +56,7 @@ dec_self_attn_kernel(DecodeGeom g, int layer, const T* __restrict__ qkv, T* __re
   const int b = row / g.K, kb = row - b * g.K;
   const int step = *d_step;
   const int H = g.H, D = g.D;
-  const int nd = D / 32;                       // dims per lane (2 for D=64, 4 for D=128)
+  constexpr int nd = ND;                       // dims per lane (2 for D=64, 4 for D=128)
   const T* qrow = qkv + (int64_t)row * 3 * H + h * D;
   float q[4], kn[4], vn[4];
 #pragma unroll
@@ -77,6 +78,18 @@ dec_self_attn_kernel(DecodeGeom g, int layer, const T* __restrict__ qkv, T* __re
       if (u < nd) { kc[lane + 32 * u] = from_f32<T>(kn[u]); vc[lane + 32 * u] = from_f32<T>(vn[u]); }
   }
   __syncwarp();
+  constexpr int VB = 16;                       // value rows in flight per batch
+  float vv[VB][ND];
+  auto load_v = [&](int t0) {
+#pragma unroll
+    for (int i = 0; i < VB; ++i) {
+      const int t = t0 + i;
+      const T* vc = cache_ptr(1, t < step ? t : 0);
+#pragma unroll
+      for (int u = 0; u < ND; ++u) vv[i][u] = (t < step) ? to_f32(vc[lane + 32 * u]) : 0.f;
+    }
+  };
+  load_v(0);
   const float scale_div = sqrtf((float)D);
   // score of the new position: one reduction over the lanes' dims
   float part = 0.f;
@@ -108,21 +121,14 @@ dec_self_attn_kernel(DecodeGeom g, int layer, const T* __restrict__ qkv, T* __re
   const float sum = warp_sum(e);
   const float pr = e / sum;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int t0 = 0; t0 < step; t0 += 6) {
-    float vv[6][4];
+  for (int t0 = 0; t0 < step; t0 += VB) {
+    if (t0 > 0) load_v(t0);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const int t = t0 + i;
-      const T* vc = cache_ptr(1, t < step ? t : 0);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) vv[i][u] = (u < nd && t < step) ? to_f32(vc[lane + 32 * u]) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < VB; ++i) {
       const float pt = __shfl_sync(0xffffffffu, pr, (t0 + i) & 31);
       if (t0 + i < step) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] = fmaf(pt, vv[i][u], acc[u]);
+        for (int u = 0; u < ND; ++u) acc[u] = fmaf(pt, vv[i][u], acc[u]);
       }
     }
   }
@@ -514,8 +520,13 @@ int launch_dec_self_attn(int dtype, const DecodeGeom& g, int layer, const void* 
   if (g.D != 64 && g.D != 128) throw std::runtime_error("dec_self_attn: head_dim must be 64 or 128");
   if (g.T > kMaxSteps) throw std::runtime_error("dec_self_attn: at most 32 cached positions");
   dim3 grid(g.B * g.K, (g.heads + 3) / 4);
-  if (dtype == kF32) launch_k(dec_self_attn_kernel<float>, grid, dim3(128), 0, stream, g, layer, (const float*)qkv, (float*)self_cache, d_step, (float*)out);
-  else launch_k(dec_self_attn_kernel<bf16>, grid, dim3(128), 0, stream, g, layer, (const bf16*)qkv, (bf16*)self_cache, d_step, (bf16*)out);
+  if (g.D == 64) {
+    if (dtype == kF32) launch_k(dec_self_attn_kernel<float, 2>, grid, dim3(128), 0, stream, g, layer, (const float*)qkv, (float*)self_cache, d_step, (float*)out);
+    else launch_k(dec_self_attn_kernel<bf16, 2>, grid, dim3(128), 0, stream, g, layer, (const bf16*)qkv, (bf16*)self_cache, d_step, (bf16*)out);
+  } else {
+    if (dtype == kF32) launch_k(dec_self_attn_kernel<float, 4>, grid, dim3(128), 0, stream, g, layer, (const float*)qkv, (float*)self_cache, d_step, (float*)out);
+    else launch_k(dec_self_attn_kernel<bf16, 4>, grid, dim3(128), 0, stream, g, layer, (const bf16*)qkv, (bf16*)self_cache, d_step, (bf16*)out);
+  }
   return 1;
 }
 

@@ -340,7 +340,7 @@ struct Exec {
         const bool prof = c->profiling && M >= c->prof_min_rows && c->prof_used < c->prof_pool.size() &&
                           cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone;
         if (prof) cudaEventRecord(c->prof_pool[c->prof_used].a, s);
-        c->launches += launch_gemm_tc(a, c->num_sms, s);
+        c->launches += launch_gemm_tc(a, c->num_sms, s, (c->cfg.flags & GSTVD_FLAG_SHARED_SM_GEMM) != 0);
         if (prof) {
           auto& r = c->prof_pool[c->prof_used++];
           cudaEventRecord(r.b, s);

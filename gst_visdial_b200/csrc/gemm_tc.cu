@@ -34,8 +34,12 @@ namespace {
 constexpr int BM = 128;          // rows per tile  (UMMA M)
 constexpr int BK = 64;           // k per stage: 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kEpiWarps = 16;         // 4 per TMEM lane quadrant: the epilogue is ALU/latency bound, it needs the warps
-constexpr int kThreads = (2 + kEpiWarps) * 32;
+// Epilogue warps: 16 (4 per TMEM lane quadrant) for the throughput configurations - the epilogue is ALU/latency bound and
+// needs the warps; 4 (one per quadrant) for the "skinny" decode configuration, whose 6-warp CTA with ~100 KB of shared
+// memory lets TWO CTAs share an SM: decode GEMMs (M = 320) are latency bound, so a co-resident CTA - the next GEMM of the
+// same stream under PDL, or another stream's - fills the SM time this one spends waiting.
+constexpr int kEpiWarpsWide = 16;
+constexpr int kEpiWarpsSkinny = 4;
 constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;   // 4 s: far beyond any legitimate wait
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -169,11 +173,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BN> struct TileCfg {
+template <int BN, int EW> struct TileCfg {
+  static constexpr bool kSkinny = EW == kEpiWarpsSkinny;
+  static constexpr int kThreads = (2 + EW) * 32;
   // k-chunks (64 elements each) per pipeline stage.  The narrow tiles serve the M <= 384 decode GEMMs, whose main loop is
   // bound by the RATE of TMA operations issued by one thread (~0.13 us each), not by bytes: one 3-D box
   // {64, rows, 4 chunks} moves four k-blocks per operation.
-  static constexpr int kCK = BN <= 64 ? 4 : 1;
+  static constexpr int kCK = kSkinny ? 2 : (BN <= 64 ? 4 : 1);
   static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 2);
   static constexpr int kAChunk = BM * BK * 2;                  // one 128-row x 64-element SW128 tile
   static constexpr int kBChunk = BN * BK * 2;
@@ -182,8 +188,12 @@ template <int BN> struct TileCfg {
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // power of two for BN in {16,32,64,128,256}
   static constexpr int kBarBytes = 256;
   static constexpr int kStageWords = 32 * 33;                   // per epilogue warp: 32 rows x 32 words, padded rows
-  static constexpr int kStagingBytes = 8 * kStageWords * 4;    // 33 KB: 4 x 8 KB (bf16) / 2 x 16 KB (fp32) TMA-store tiles, or 8 generic tiles
-  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kBarBytes + kStagingBytes + 1024;   // +1024: alignment slack
+  // wide: 33 KB = 4 x 8 KB (bf16) / 2 x 16 KB (fp32) TMA-store tiles, or 8 generic tiles; skinny: one group, 4 generic tiles
+  static constexpr int kStagingBytes = (kSkinny ? 4 : 8) * kStageWords * 4;
+  // The wide configurations keep 1 KB of alignment slack; the skinny ones must fit twice into an SM (2 x (bytes + 1 KB
+  // reserved) <= 228 KB) and rely on the 1024-byte alignment of the dynamic shared-memory window (checked at run time).
+  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kBarBytes + kStagingBytes + (kSkinny ? 0 : 1024);
+  static_assert(!kSkinny || 2 * (kSmemBytes + 1024) <= 233472, "skinny configuration must fit two CTAs per SM");
 };
 
 // GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.25 (|error| <= 2.5e-5, two orders of magnitude below
@@ -372,15 +382,17 @@ __device__ __forceinline__ void epilogue_tma_block(const GemmArgs& p, const CUte
   }
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int EW>
+__global__ void __launch_bounds__((2 + EW) * 32, EW == kEpiWarpsSkinny ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                const __grid_constant__ CUtensorMap tm_c, const GemmArgs p) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, EW>;
   constexpr int kStages = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
+  constexpr int kGroups = EW / 4;                               // epilogue groups of 4 warps (one warp per TMEM lane quadrant)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // 128B-swizzle atoms need 1024-byte alignment
+  if (Cfg::kSkinny && base != raw) __trap();                    // no slack in the skinny layout
   const uint32_t a_base = base;
   const uint32_t b_base = base + kStages * Cfg::kABytes;
   const uint32_t stage_base = b_base + kStages * Cfg::kBBytes;   // epilogue staging (1024-byte aligned: TMA-store source)
@@ -408,7 +420,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     tma_prefetch_desc(&tm_b);
     if (p.tma_store) tma_prefetch_desc(&tm_c);
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps * 32); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EW * 32); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -501,9 +513,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const int quad = warp & 3;                        // TMEM lane quadrant this warp may access
     const int grp = e >> 2;                           // 4 groups of 4 warps (one warp per quadrant = 128 accumulator rows)
     const int half = grp;                             // the generic (non-TMA) path only uses groups 0 and 1
-    constexpr int kColsPerHalf = BN >= 64 ? BN / 2 : BN;
-    const int c_begin = (BN >= 64) ? half * kColsPerHalf : 0;
-    const int c_end = (grp >= 2) ? 0 : ((BN >= 64) ? c_begin + kColsPerHalf : (half == 0 ? BN : 0));
+    constexpr bool kSplit = BN >= 64 && kGroups >= 2;       // generic path: two groups share the columns of a wide tile
+    constexpr int kColsPerHalf = kSplit ? BN / 2 : BN;
+    const int c_begin = kSplit ? half * kColsPerHalf : 0;
+    const int c_end = (grp >= 2) ? 0 : (kSplit ? c_begin + kColsPerHalf : (half == 0 ? BN : 0));
     uint32_t* stage = reinterpret_cast<uint32_t*>(smem_gen + (stage_base - base)) + (e & 7) * Cfg::kStageWords;
     int iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
@@ -525,9 +538,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const uint32_t tq = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
         if (p.out_f32) {
           // fp32 rows of 32 columns are 128 bytes: two 16 KB staging tiles, groups 0 and 1 only
-          if (grp < 2) {
+          constexpr int kFGroups = kGroups < 2 ? kGroups : 2;
+          if (grp < kFGroups) {
             const uint32_t stg = stage_base + grp * 16384;
-            for (int j = grp; j < BN / 32; j += 2) {
+            for (int j = grp; j < BN / 32; j += kFGroups) {
               const int col0 = n_blk * BN + j * 32;
               if (col0 >= p.N) break;                       // uniform across the group
               epilogue_tma_block<float, 32>(p, &tm_c, tq + j * 32, stg, m_blk * BM, col0, r, grp, issuer);
@@ -536,7 +550,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         } else {
           // bf16 rows of 32 columns are 64 bytes: four 8 KB staging tiles, one per group
           const uint32_t stg = stage_base + grp * 8192;
-          for (int j = grp; j < BN / 32; j += 4) {
+          for (int j = grp; j < BN / 32; j += kGroups) {
             const int col0 = n_blk * BN + j * 32;
             if (col0 >= p.N) break;
             epilogue_tma_block<bf16, 32>(p, &tm_c, tq + j * 32, stg, m_blk * BM, col0, r, grp, issuer);
@@ -668,12 +682,12 @@ const CUtensorMap& get_map_hm(const void* ptr, int D, int L, int G, int64_t LB) 
   return cached_map(key, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int BN>
+template <int BN, int EW = kEpiWarpsWide>
 void launch_cfg(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, EW>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) throw std::runtime_error(std::string("gemm_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     attr_set = true;
   }
@@ -703,8 +717,9 @@ void launch_cfg(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
   }
   const int tiles_m = a.hm_tpi > 0 ? a.hm_B * a.hm_tpi : (a.M + BM - 1) / BM;
   const int tiles = tiles_m * ((a.N + BN - 1) / BN);
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(kThreads), (size_t)Cfg::kSmemBytes, stream, *ma_ptr, mb, *mc, a);
+  const int slots = Cfg::kSkinny ? 2 * num_sms : num_sms;      // resident CTAs: the kernel is persistent over the remaining tiles
+  const int grid = tiles < slots ? tiles : slots;
+  launch_k(gemm_tc_kernel<BN, EW>, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmemBytes, stream, *ma_ptr, mb, *mc, a);
 }
 
 }  // namespace
@@ -731,7 +746,7 @@ const void* tma_map_rows3(const void* ptr, int D, int L, int64_t groups, int box
   return &cached_map(key, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
+int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream, bool shared_sm) {
   if (a_in.M <= 0 || a_in.N <= 0) return 0;
   static const int dbg_env = [] { const char* e = getenv("GSTVD_GEMM_DBG"); return e ? atoi(e) : 0; }();
   static const int bn_env = [] { const char* e = getenv("GSTVD_GEMM_BN"); return e ? atoi(e) : 0; }();
@@ -757,6 +772,13 @@ int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
   }
   if (bn_env) bn = bn_env;
   if (bn <= 64 && a.K % BK != 0) bn = 128;               // the chunked (3-D box) operand view needs whole 64-element chunks
+  static const int skinny_env = [] { const char* e = getenv("GSTVD_GEMM_SKINNY"); return e ? atoi(e) : -1; }();   // A/B aid: force 0 / 1
+  const bool skinny = skinny_env >= 0 ? skinny_env != 0 : shared_sm;
+  if (tiles_m <= 4 && bn <= 64 && skinny && a.K % BK == 0 && a.hm_D == 0) {
+    if (bn == 64) launch_cfg<64, kEpiWarpsSkinny>(a, num_sms, stream);
+    else launch_cfg<32, kEpiWarpsSkinny>(a, num_sms, stream);
+    return 1;
+  }
   switch (bn) {
     case 256: launch_cfg<256>(a, num_sms, stream); break;
     case 128: launch_cfg<128>(a, num_sms, stream); break;

@@ -55,7 +55,8 @@ struct GemmArgs {
 // SIMT GEMM: dtype kF32 (all fp32) or kBF16 (bf16 operands, fp32 accumulate; debugging aid)
 int launch_gemm_simt(const GemmArgs& a, int dtype, cudaStream_t stream);
 // tcgen05 / TMEM / TMA GEMM, bf16 operands, fp32 accumulate.
-int launch_gemm_tc(const GemmArgs& a, int num_sms, cudaStream_t stream);
+// shared_sm: skinny (M <= 512) problems use the 6-warp / ~100 KB configuration of which two CTAs fit one SM
+int launch_gemm_tc(const GemmArgs& a, int num_sms, cudaStream_t stream, bool shared_sm = false);
 void gemm_tc_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes
 
 struct AttnArgs {
