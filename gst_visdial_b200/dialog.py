@@ -39,10 +39,15 @@ def _model_call(model, st, dec_input_ids, **kw):
 
 
 def generate_dialogs(a_model, batch, q_model=None, questions=None, num_rounds=10, a_kwargs=None, q_kwargs=None,
-                     with_ppl=True, device=None) -> DialogResult:
+                     with_ppl=True, device=None, trim_history=True, max_new_tokens=18) -> DialogResult:
     """``batch`` uses the reference dataloader's keys (generate.py:95-111).  Either ``q_model`` or ``questions``
     (int64 [B, num_rounds, 18], zero padded, each ending in [SEP]) must be given.  ``a_kwargs`` / ``q_kwargs`` are the
-    decoding kwargs of EncoderDecoderModel.forward; defaults are generate.py:138-141 / :177-180."""
+    decoding kwargs of EncoderDecoderModel.forward; defaults are generate.py:138-141 / :177-180.
+
+    ``trim_history``: the encoder runs on ceil32(longest history) text positions instead of all ``max_seq_len`` (see
+    ``enc_valid_len`` in EncoderDecoderModel.forward).  The bound is kept on the HOST - caption lengths are read once at the
+    start, every round adds the question length (or ``max_new_tokens`` for a generated question) and ``max_new_tokens`` for
+    the answer - so no round waits for the device.  Token ids, perplexities and flags are identical with or without it."""
     a_kwargs = dict(a_kwargs or dict(temperature=0.7, top_k=7, top_p=0.0, ngram_blocking_size=0))
     q_kwargs = dict(q_kwargs or dict(temperature=0.7, top_k=7, top_p=0.0, ngram_blocking_size=4))
     am = _unwrap(a_model)
@@ -60,16 +65,34 @@ def generate_dialogs(a_model, batch, q_model=None, questions=None, num_rounds=10
     enc_len = (st["ids"] != 0).sum(-1).to(torch.int32)
     abnormal = torch.zeros(B, dtype=torch.int32, device=dev)
     dec_start = batch["dec_input_ids"].to(dtype=torch.int64, **nb)
+    q_host = None                                               # [B, rounds] question lengths, read before the copy to the device
     if questions is not None:
+        if trim_history and q_model is None:
+            q_host = (questions != 0).sum(-1).cpu().to(torch.int64)
         questions = questions.to(dtype=torch.int64, **nb)
     elif q_model is None:
         raise ValueError("generate_dialogs needs q_model or questions")
     ques_all, ans_all, ppl_all = [], [], []
     mode = am.params["mode"]
+    Lmax = st["ids"].shape[1]
+    ub = None                                                   # host-side per-row upper bound of the history length
+    if trim_history:
+        ub = (batch["enc_input_ids"] != 0).sum(-1).cpu().to(torch.int64)      # one read at the start (free for host inputs)
+
+    def bound():
+        return int(ub.max().clamp(max=Lmax)) if ub is not None else None
+
     for rnd in range(num_rounds):
-        ques = questions[:, rnd].contiguous() if q_model is None else _model_call(q_model, st, dec_start, **q_kwargs)
+        if q_model is None:
+            ques = questions[:, rnd].contiguous()
+        else:
+            ques = _model_call(q_model, st, dec_start, enc_valid_len=bound(), **q_kwargs)
         eng.splice(st["ids"], st["seg"], st["mask"], enc_len, ques, segment_value=-1, strip_sep=False, abnormal=abnormal)
-        ans = _model_call(a_model, st, dec_start, **a_kwargs)
+        if ub is not None:
+            ub = ub + (q_host[:, rnd] if q_host is not None else max_new_tokens)
+        ans = _model_call(a_model, st, dec_start, enc_valid_len=bound(), **a_kwargs)
+        if ub is not None:
+            ub = ub + max_new_tokens
         if with_ppl:
             am.params["mode"] = "train"                      # the reference's mode-flip trick (generate.py:185,211)
             try:

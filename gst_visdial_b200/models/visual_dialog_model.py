@@ -27,6 +27,10 @@ class EncoderDecoderModel(_EngineOwner, nn.Module):
     Extra keyword arguments (all default to the reference behaviour):
       num_beams=1        >1 switches the token selection to beam search (contract: oracle/beam.py)
       seed=None          sampling seed (a per-call counter when None)
+      enc_valid_len=None   upper bound (python int) on the number of leading history positions that hold a token in ANY row.
+                         The encoder, the cross-K/V prefill and the cross-attention then run on ceil32(bound) text positions
+                         instead of max_seq_len: positions past the last token are padding whose keys carry zero weight and
+                         whose rows nobody reads, so every valid position is bit-identical.
       reuse_encoder=False  reuse the encoder/cross-KV state left by the previous call (the caller guarantees the
                          encoder inputs are unchanged, e.g. generate.py's perplexity pass right after the answer pass)
     """
@@ -90,7 +94,14 @@ class EncoderDecoderModel(_EngineOwner, nn.Module):
         eng = self._engine(enc_input_ids.device)
         B = enc_input_ids.shape[0]
         if not decoding_kwargs.get("reuse_encoder", False):
-            enc = eng.encode(enc_input_ids, enc_image_features, enc_image_spatials, enc_segments, enc_attention_mask, enc_image_mask)
+            hint = decoding_kwargs.get("enc_valid_len")
+            ids_e, seg_e, att_e = enc_input_ids, enc_segments, enc_attention_mask
+            if hint is not None:
+                Lt = enc_input_ids.shape[1]
+                Lt_eff = min(Lt, max(32, (int(hint) + 31) // 32 * 32))
+                if Lt_eff < Lt:
+                    ids_e, seg_e, att_e = ids_e[:, :Lt_eff], seg_e[:, :Lt_eff], (att_e[:, :Lt_eff] if att_e is not None else None)
+            enc = eng.encode(ids_e, enc_image_features, enc_image_spatials, seg_e, att_e, enc_image_mask)
             eng.prefill_cross(B, enc["Le"])
 
         if 'train' in self.params['mode'] or 'eval' in self.params['mode']:

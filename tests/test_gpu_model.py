@@ -324,6 +324,24 @@ def test_dialog_loop_beam_config2_shape(tiny_cfgs, tiny_sd):
     assert torch.equal(res.enc_input_ids.cpu(), rids)
 
 
+def test_history_trimming_is_exact(tiny_cfgs, tiny_sd):
+    """Encoder on ceil32(longest history) positions vs all max_seq_len positions: identical ids, ppl, history and flags."""
+    from gst_visdial_b200 import synthetic as S, weights as W
+    from gst_visdial_b200.dialog import generate_dialogs
+    enc_cfg, dec_cfg = tiny_cfgs
+    for dtype in ("fp32", "bf16"):
+        a_model, _ = _build_model(W.TINY_ENC_CONFIG, W.TINY_DEC_CONFIG, tiny_sd, dtype)
+        B, rounds = 4, 4
+        batch = S.synthetic_batch(0, B, vocab_size=enc_cfg.vocab_size, v_feature_size=enc_cfg.v_feature_size)
+        ques = torch.stack([torch.stack([S.synthetic_utterance(i, r, enc_cfg.vocab_size) for r in range(rounds)]) for i in range(B)])
+        kw = dict(temperature=1.0, top_k=1, top_p=0.0, ngram_blocking_size=0, num_beams=3)
+        r1 = generate_dialogs(a_model, batch, questions=ques, num_rounds=rounds, a_kwargs=kw, with_ppl=True, trim_history=True)
+        r0 = generate_dialogs(a_model, batch, questions=ques, num_rounds=rounds, a_kwargs=kw, with_ppl=True, trim_history=False)
+        assert torch.equal(r1.answers, r0.answers) and torch.equal(r1.enc_input_ids, r0.enc_input_ids)
+        assert torch.equal(r1.abnormal, r0.abnormal)
+        assert torch.equal(r1.answer_ppl.nan_to_num(-1.0), r0.answer_ppl.nan_to_num(-1.0)), dtype
+
+
 def test_generate_cli_synthetic(tmp_path):
     """generate.py end to end (questioner + teacher, sampling with 4-gram blocking, ppl) on the tiny configs."""
     import json
