@@ -765,9 +765,17 @@ int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream, bool 
       if (tiles_m * ((a.N + cand[i] - 1) / cand[i]) <= num_sms) { bn = cand[i]; break; }
     }
   } else {
-    // largest N tile that still gives every SM a tile; small problems fall through to the narrowest tile
-    for (int i = 0; i < 3; ++i) {
-      if (a.N >= cand[i] && tiles_m * ((a.N + cand[i] - 1) / cand[i]) >= num_sms) { bn = cand[i]; break; }
+    // Throughput problems: the tile width that maximises (wave efficiency) x (per-tile efficiency of that width).  Wide tiles
+    // run the tensor pipe best, but a persistent grid of 148 CTAs wastes the last wave: e.g. M = 2048, N = 3072 is 192 tiles
+    // of 256 columns (two waves, 65 % full) or 384 tiles of 128 columns (three waves, 86 % full).
+    const double tile_eff[4] = {1.0, 0.88, 0.6, 0.35};
+    double best = -1.0;
+    for (int i = 0; i < 4; ++i) {
+      const int64_t tiles = (int64_t)tiles_m * ((a.N + cand[i] - 1) / cand[i]);
+      const int64_t waves = (tiles + num_sms - 1) / num_sms;
+      const double used = (double)a.N / ((double)((a.N + cand[i] - 1) / cand[i]) * cand[i]);     // columns of the last tile that exist
+      const double eff = (double)tiles / (double)(waves * num_sms) * tile_eff[i] * used;
+      if (eff > best + 1e-9) { best = eff; bn = cand[i]; }
     }
   }
   if (bn_env) bn = bn_env;
