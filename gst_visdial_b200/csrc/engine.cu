@@ -412,6 +412,15 @@ void conn_layer_fwd(Exec& X, const ConnLayer& L, int B, int Lt, int Lv, const fl
 
 void check_ready(gstvd_ctx* c) { if (!c->finalized) throw StateError("weights not finalized: call gstvd_finalize_weights first"); }
 
+// Programmatic dependent launch for every launch_k kernel enqueued in the scope: each of them starts with its prologue
+// (barrier init, TMEM allocation, weight / gamma prefetch) while the predecessor drains and calls griddepcontrol.wait before
+// it touches the predecessor's output.  Kernels launched with <<<>>> inside the scope keep full stream ordering.
+struct PdlScope {
+  bool prev;
+  explicit PdlScope(bool on) : prev(pdl_flag()) { pdl_flag() = on; }
+  ~PdlScope() { pdl_flag() = prev; }
+};
+
 void do_encode(gstvd_ctx* c, int B, int Lt, int Lv, const int64_t* ids, const int64_t* seg, const float* att, const float* feat,
                const float* loc, const float* imask, float* out_t, float* out_v, float* out_fused, float* out_fused_mask,
                float* out_nsp, cudaStream_t s) {
@@ -419,6 +428,7 @@ void do_encode(gstvd_ctx* c, int B, int Lt, int Lv, const int64_t* ids, const in
   if (B < 1 || B > c->B_max || Lt < 1 || Lt > c->Lt_max || Lv < 1 || Lv > c->Lv_max)
     throw InvalidArg(fmt("encode: shape B=%d Lt=%d Lv=%d exceeds capacity (%d, %d, %d)", B, Lt, Lv, c->B_max, c->Lt_max, c->Lv_max));
   if (!ids || !feat || !loc) throw InvalidArg("encode: input_ids / image_feat / image_loc must not be NULL");
+  PdlScope pdl_scope(!(c->cfg.flags & GSTVD_FLAG_NO_PDL));
   if (Lt > c->cfg.max_position_embeddings) throw InvalidArg("encode: Lt exceeds max_position_embeddings");
   Exec X{c, s};
   const int H = c->H, Hv = c->Hv, Mt = B * Lt, Mv = B * Lv;
@@ -477,6 +487,7 @@ void do_prefill(gstvd_ctx* c, int B, int Le, const float* enc_hidden, const floa
   check_ready(c);
   if (c->dec_layers == 0) throw StateError("prefill_cross: encoder-only context");
   if (B < 1 || B > c->B_max || Le < 1 || Le > c->Le_max) throw InvalidArg("prefill_cross: shape exceeds capacity");
+  PdlScope pdl_scope(!(c->cfg.flags & GSTVD_FLAG_NO_PDL));
   Exec X{c, s};
   const int H = c->H;
   if (enc_hidden) {
@@ -517,7 +528,6 @@ BeamBuffers beam_buffers(gstvd_ctx* c) {
 void decode_step(gstvd_ctx* c, const DecodeGeom& g, const gstvd_gen_params& gp, const int64_t* hist_ids, const int64_t* hist_seg,
                  int Lh, cudaStream_t s) {
   Exec X{c, s};
-  struct PdlScope { bool prev; explicit PdlScope(bool on) : prev(pdl_flag()) { pdl_flag() = on; } ~PdlScope() { pdl_flag() = prev; } };
   PdlScope pdl_scope(!(c->cfg.flags & GSTVD_FLAG_NO_PDL));
   const int H = c->H, M = g.B * g.K;
   const int* d_step = (const int*)c->d_step.p;
@@ -644,6 +654,7 @@ void do_score(gstvd_ctx* c, int B, int L, int64_t* dec_ids, const float* dec_mas
   if (c->cross_B != B / options) throw StateError(fmt("score: cross K/V prefilled for %d images, asked for %d", c->cross_B, B / options));
   if (L < 1 || L > c->Ldec_max || L > c->cfg.max_position_embeddings) throw InvalidArg("score: L out of range");
   if (!dec_ids) throw InvalidArg("score: dec_ids is NULL");
+  PdlScope pdl_scope(!(c->cfg.flags & GSTVD_FLAG_NO_PDL));
   Exec X{c, s};
   const int H = c->H, M = B * L, D = H / c->dec_heads, Le = c->cross_Le;
   const int64_t* lab = labels;
