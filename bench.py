@@ -251,7 +251,7 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize(dev)
 
-    host_ms = [0.0]
+    host_ms = [0.0, 0.0]
 
     def launches_total():
         return sum(sl["eng"].launch_count for sl in slots)
@@ -267,7 +267,7 @@ def main():
         e0.record(cur)
         for sl in slots:
             sl["stream"].wait_event(e0)
-        t_host = time.perf_counter()
+        t_host, c_host = time.perf_counter(), time.process_time()
         # one submitting host thread per stream: a single thread blocks on the launch queue of one stream (back-pressure of
         # ~2.7k launches per round) and starves the others; the C ABI / torch calls release the GIL
         outs = [None] * S_
@@ -297,7 +297,8 @@ def main():
             abn = torch.cat([o[1].to(dev) for o in mine], 0)
             g_ans, g_abn = D.gather_results([ans, abn], [ans.shape[0]] * world)
             out = (g_ans, g_abn)
-        host_ms[0] = (time.perf_counter() - t_host) * 1e3 / steps      # CPU wall time to ENQUEUE one step (no device wait inside)
+        host_ms[0] = (time.perf_counter() - t_host) * 1e3 / steps      # wall time the submitting threads needed per step
+        host_ms[1] = (time.process_time() - c_host) * 1e3 / steps      # CPU time (all threads of this process) per step
         for sl in slots:
             cur.wait_stream(sl["stream"])
         e1.record(cur)
@@ -321,7 +322,7 @@ def main():
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     ms, launches, prof, out = timed(False, False, a.steps, S_ == 1)
-    host_issue_ms = host_ms[0]
+    host_issue_ms, host_cpu_ms = host_ms[0], host_ms[1]
     clocks = sampler.stop() if sampler else None
     if S_ > 1:
         # With several batches in flight the event pairs around one stream's GEMMs also span other streams' kernels, so the
@@ -360,7 +361,7 @@ def main():
             "config": {"workload": workload_name(a), "global_batch": B * world, "rounds": a.rounds, "beams": a.beams,
                        "parallelism": f"dp{world}: independent image shards, one final NCCL all_gather of token ids",
                        "history_positions": "all 256" if a.no_trim else "ceil32(longest history in the batch): padded positions are never read, results identical",
-                       "streams_per_gpu": S_, "batch_per_forward": B, "host_enqueue_ms_per_step": host_issue_ms,
+                       "streams_per_gpu": S_, "batch_per_forward": B, "host_enqueue_ms_per_step": host_issue_ms, "host_cpu_ms_per_step": host_cpu_ms,
                        "l2": "no explicit flush: each step streams >1.5 GB (0.78 GB bf16 weights, 0.69 GB cross-KV, activations), "
                              "far beyond the 126 MB L2",
                        "end_to_end_tflops": value * TF_PER_DIALOG, "tf_per_dialog": TF_PER_DIALOG},
