@@ -170,11 +170,34 @@ def run_reference(a, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything that libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr; the ONE JSON line is written to
+    the original stdout by _emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _quiet_stdout()
     a = parse()
     from gst_visdial_b200 import dist as D
     if a.impl == "reference":
@@ -384,7 +407,7 @@ def main():
             line["cpu_baseline"] = {"value": 1.0 / (a.rounds * t_round), "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"1 image x 1 round (of {a.rounds}), beam {a.beams}, fp32, reference algorithm (no KV cache, "
                                               f"discarded heads evaluated), mean of 3 repeats = {t_round:.2f} s, scaled x{a.rounds} to a dialog"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
