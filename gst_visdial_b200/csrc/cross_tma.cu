@@ -215,6 +215,227 @@ dec_cross_tma_kernel(const __grid_constant__ CUtensorMap tm, DecodeGeom g, int l
   }
 }
 
+// ---- variant 2: one 16-warp CTA per SM, two (K, V) stages, scores and probabilities never leave the registers ----
+// With two CTAs per SM and one K + one V buffer each (above) every CTA alternates between waiting for a transfer and a
+// burst of math in lockstep with all the others, and the math itself - scores to shared memory, a three-pass softmax by
+// 5 of the warps, probabilities back through shared memory - costs ~8 k warp instructions per item: 44 % of the HBM rate.
+// Here each SM owns 4 x 40 KB of buffers: item i+1 was requested while item i-1 finished and streams during the whole of
+// item i.  A warp owns at most two 16-key groups; the m16n8k16 accumulator layout of its scores IS the A-operand layout
+// of the probabilities, so after one block-wide max exchange (8 floats per warp) it exponentiates in registers and
+// multiplies by its V rows directly; partial contexts and partial sums meet in shared memory once per item.
+// Template: kX2Warps warps, kStages (K, V) buffer pairs, kX2Groups key groups per warp.  <16, 2, 2> is the one-CTA-per-SM
+// form described above; <8, 1, 3> fits two CTAs per SM with single buffers (K re-armed after the scores, V after the
+// context product) - measured faster: two independent item pipelines per SM hide each other's barrier waits.
+template <int kX2Warps, int kStages, int kX2Groups>
+struct X2Cfg {
+  static constexpr int kThreads = kX2Warps * 32;
+  static constexpr int kSmem = 2 * kStages * kXtBufBytes + 2 * kXtLeP * 4 + kX2Warps * 8 * 64 * 4 + 2 * kX2Warps * 8 * 4 + 64 + 1024;
+  static_assert(kX2Warps * kX2Groups * 16 >= kXtLeP, "every key group needs an owner");
+};
+
+template <int kX2Warps, int kStages, int kX2Groups>
+__global__ void __launch_bounds__(kX2Warps * 32, kStages == 1 ? 2 : 1)
+dec_cross_tma2_kernel(const __grid_constant__ CUtensorMap tm, DecodeGeom g, int layer, const bf16* __restrict__ q,
+                      const float* __restrict__ enc_mask, const int* __restrict__ cross_len, bf16* __restrict__ out) {
+  extern __shared__ uint8_t xt_raw[];
+  const uint32_t raw = smem_u32(xt_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;             // swizzled boxes need 1024-byte alignment
+  uint8_t* gen = xt_raw + (base - raw);
+  // stage s: K at base + s * 80 KB, V 40 KB behind it
+  constexpr int kX2Threads = kX2Warps * 32;
+  float* madd = reinterpret_cast<float*>(gen + 2 * kStages * kXtBufBytes);         // [2][304] additive mask rows (log2 domain)
+  float* part = madd + 2 * kXtLeP;                                       // [16][8][64] partial contexts
+  float* wmax = part + kX2Warps * 8 * 64;                                // [16][8] per-warp score maxima
+  float* wsum = wmax + kX2Warps * 8;                                     // [16][8] per-warp sums of exp
+  const uint32_t bar0 = smem_u32(wsum + kX2Warps * 8);                   // K0, V0, K1, V1
+  auto k_buf = [&](int s) { return base + (uint32_t)s * 2u * kXtBufBytes; };
+  auto v_buf = [&](int s) { return base + (uint32_t)s * 2u * kXtBufBytes + kXtBufBytes; };
+  auto bar_k = [&](int s) { return bar0 + 16u * s; };
+  auto bar_v = [&](int s) { return bar0 + 16u * s + 8u; };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int beam = lane >> 2, p4 = lane & 3, mi = lane >> 3;
+  const int items = g.B * g.heads;
+  if (tid == 0) {
+    tma_prefetch_desc(&tm);
+    for (int i = 0; i < 2 * kStages; ++i) mbar_init(bar0 + 8u * i, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+
+  auto keys_of = [&](int b) { const int n = cross_len ? cross_len[b] : g.Le; return n < 1 ? 1 : (n > g.Le ? g.Le : n); };
+  // warp 0: request K and V of `item` into stage s; lanes 0..nb-1 fetch the K boxes, lanes 8..8+nb-1 the V boxes
+  auto issue = [&](int item, int kv, int s, int nk_item) {
+    const int b = item / g.heads, h = item - b * g.heads;
+    const int nb = (nk_item + kXtRows - 1) / kXtRows;
+    const uint32_t bar = kv ? bar_v(s) : bar_k(s), buf = kv ? v_buf(s) : k_buf(s);
+    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nb * kXtBoxBytes));
+    __syncwarp();
+    const int z = ((layer * g.B + b) * 2 + kv) * g.heads + h;
+    if (lane < nb) tma_load_3d(buf + lane * kXtBoxBytes, &tm, 0, lane * kXtRows, z, bar);
+  };
+  // mask entries of this thread (kMaskPer x threads >= 304): the RAW values are loaded early and only converted when they
+  // are stored, so the load latency is not on the critical path
+  constexpr int kMaskPer = (kXtLeP + kX2Threads - 1) / kX2Threads;
+  float mraw[kMaskPer];
+  auto load_mask = [&](int b) {
+#pragma unroll
+    for (int i = 0; i < kMaskPer; ++i) {
+      const int j = tid + i * kX2Threads;
+      mraw[i] = (enc_mask && j < g.Le) ? enc_mask[(int64_t)b * g.Le + j] : 1.f;
+    }
+  };
+  auto store_mask = [&](float* dst) {
+#pragma unroll
+    for (int i = 0; i < kMaskPer; ++i) {
+      const int j = tid + i * kX2Threads;
+      if (j < kXtLeP) dst[j] = (j < g.Le) ? (1.0f - mraw[i]) * (-1e9f * kLog2e) : -INFINITY;
+    }
+  };
+  uint32_t qa0[4], qa2[4];
+  auto load_q = [&](int item) {
+    const int b = item / g.heads, h = item - b * g.heads;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) { qa0[kk] = 0u; qa2[kk] = 0u; }
+    if (beam < g.K) {
+      const bf16* qp = q + ((int64_t)(b * g.K + beam)) * g.H + h * 64 + p4 * 2;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        qa0[kk] = *reinterpret_cast<const uint32_t*>(qp + kk * 16);
+        qa2[kk] = *reinterpret_cast<const uint32_t*>(qp + kk * 16 + 8);
+      }
+    }
+  };
+  const int first = blockIdx.x, stride = gridDim.x;
+  if (first >= items) return;
+  // key counts of this item and the next two, fetched one item ahead of their use (a global load each)
+  int nk0 = keys_of(first / g.heads);
+  int nk1 = first + stride < items ? keys_of((first + stride) / g.heads) : 1;
+  int nk2 = first + 2 * stride < items ? keys_of((first + 2 * stride) / g.heads) : 1;
+  if (warp == 0) {
+    issue(first, 0, 0, nk0);                                // cross K/V, cross_len and the mask date from the prefill: safe before the wait
+    issue(first, 1, 0, nk0);
+    if (kStages > 1 && first + stride < items) { issue(first + stride, 0, 1, nk1); issue(first + stride, 1, 1, nk1); }
+  }
+  load_mask(first / g.heads);
+  store_mask(madd);
+  pdl_wait();                                               // the query projection of this step is complete
+  load_q(first);
+
+  const float sc = kLog2e / 8.0f;                           // scores / sqrt(64), log2 domain
+  int it = 0;
+  for (int item = first; item < items; item += stride, ++it) {
+    const int s = it % kStages, mb = it & 1;               // buffer stage; mask-row buffer
+    const uint32_t phase = (uint32_t)(it / kStages) & 1u;
+    const int ahead = item + kStages * stride;               // the item that will reuse this stage
+    const int nk_ahead = kStages == 1 ? nk1 : nk2;
+    const int b = item / g.heads, h = item - b * g.heads;
+    const int nk = nk0;
+    const int ngroups = (nk + 15) >> 4;
+    const int nw = ngroups < kX2Warps ? ngroups : kX2Warps;  // warps that own at least one key group
+    const int next = item + stride;
+    const int nk3 = item + 3 * stride < items ? keys_of((item + 3 * stride) / g.heads) : 1;   // used two iterations from now
+    const float* md = madd + mb * kXtLeP;
+    const uint32_t kb_s = k_buf(s), vb_s = v_buf(s);
+    uint32_t a_q0[4], a_q2[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) { a_q0[kk] = qa0[kk]; a_q2[kk] = qa2[kk]; }
+    if (next < items) load_mask(next / g.heads);
+    __syncthreads();                                        // (1) mask row visible; the previous item's shared results have been read
+    mbar_wait(bar_k(s), phase);
+    // ---- scores of this warp's key groups: s[gi][0..1] keys 16G + p4*2 + {0,1}, s[gi][2..3] the same + 8; row = beam ----
+    float sv[kX2Groups][4];
+    float mloc = -INFINITY;
+#pragma unroll
+    for (int gi = 0; gi < kX2Groups; ++gi) {
+      const int G = warp + gi * kX2Warps;
+      sv[gi][0] = sv[gi][1] = sv[gi][2] = sv[gi][3] = -INFINITY;
+      if (G < ngroups) {
+        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+        const int row = G * 16 + (mi >> 1) * 8 + (lane & 7);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t kb[4];
+          const int chunk = kk * 2 + (mi & 1);
+          ldmatrix_x4(kb, kb_s + row * 128 + ((chunk ^ (row & 7)) << 4));
+          mma_bf16_m8(c0, a_q0[kk], a_q2[kk], kb[0], kb[1]);
+          mma_bf16_m8(c1, a_q0[kk], a_q2[kk], kb[2], kb[3]);
+        }
+        const int key = G * 16 + p4 * 2;
+        const float2 m0 = *reinterpret_cast<const float2*>(md + key), m1 = *reinterpret_cast<const float2*>(md + key + 8);
+        sv[gi][0] = fmaf(c0[0], sc, m0.x); sv[gi][1] = fmaf(c0[1], sc, m0.y);
+        sv[gi][2] = fmaf(c1[0], sc, m1.x); sv[gi][3] = fmaf(c1[1], sc, m1.y);
+        mloc = fmaxf(fmaxf(mloc, fmaxf(sv[gi][0], sv[gi][1])), fmaxf(sv[gi][2], sv[gi][3]));
+      }
+    }
+    mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 1));
+    mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 2));
+    if (p4 == 0) wmax[warp * 8 + beam] = mloc;
+    __syncthreads();                                        // (2) per-warp maxima visible
+    if (warp == 0 && ahead < items) issue(ahead, 0, s, nk_ahead);   // every warp is past its scores: the K buffer is free
+    if (next < items) {
+      load_q(next);                                         // in flight during the rest of this item
+      store_mask(madd + (mb ^ 1) * kXtLeP);
+    }
+    float gm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < kX2Warps; ++w) gm = fmaxf(gm, w < nw ? wmax[w * 8 + beam] : -INFINITY);   // independent loads
+    // ---- probabilities (un-normalised, <= 1) as the A operand of the context product ----
+    uint32_t pa0[kX2Groups], pa2[kX2Groups];
+    float sloc = 0.f;
+#pragma unroll
+    for (int gi = 0; gi < kX2Groups; ++gi) {
+      const float e0 = ex2_approx(sv[gi][0] - gm), e1 = ex2_approx(sv[gi][1] - gm);
+      const float e2 = ex2_approx(sv[gi][2] - gm), e3 = ex2_approx(sv[gi][3] - gm);   // 2^(-inf) = 0: groups not owned, keys past Le
+      sloc += (e0 + e1) + (e2 + e3);
+      __nv_bfloat162 lo = __floats2bfloat162_rn(e0, e1), hi = __floats2bfloat162_rn(e2, e3);
+      pa0[gi] = *reinterpret_cast<uint32_t*>(&lo);
+      pa2[gi] = *reinterpret_cast<uint32_t*>(&hi);
+    }
+    sloc += __shfl_xor_sync(0xffffffffu, sloc, 1);
+    sloc += __shfl_xor_sync(0xffffffffu, sloc, 2);
+    if (p4 == 0) wsum[warp * 8 + beam] = sloc;
+    mbar_wait(bar_v(s), phase);
+    // ---- context: O[beam][d] += P[beam][keys of the group] V[keys][d] ----
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+#pragma unroll
+    for (int gi = 0; gi < kX2Groups; ++gi) {
+      const int G = warp + gi * kX2Warps;
+      if (G < ngroups) {
+        const int row = G * 16 + (mi & 1) * 8 + (lane & 7);
+#pragma unroll
+        for (int dt = 0; dt < 8; dt += 2) {
+          uint32_t vb[4];
+          const int chunk = dt + (mi >> 1);
+          ldmatrix_x4_trans(vb, vb_s + row * 128 + ((chunk ^ (row & 7)) << 4));
+          mma_bf16_m8(o[dt], pa0[gi], pa2[gi], vb[0], vb[1]);
+          mma_bf16_m8(o[dt + 1], pa0[gi], pa2[gi], vb[2], vb[3]);
+        }
+      }
+    }
+    if (warp < nw) {
+      float* pp = part + (warp * 8 + beam) * 64 + p4 * 2;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<float2*>(pp + dt * 8) = make_float2(o[dt][0], o[dt][1]);
+    }
+    __syncthreads();                                        // (3) partial contexts / sums complete; stage s is free
+    if (warp == 0 && ahead < items) issue(ahead, 1, s, nk_ahead);
+    for (int i = tid; i < g.K * 64; i += kX2Threads) {
+      const int k = i >> 6, d = i & 63;
+      float v = 0.f, t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kX2Warps; ++w) {
+        if (w < nw) { v += part[(w * 8 + k) * 64 + d]; t += wsum[w * 8 + k]; }
+      }
+      out[((int64_t)(b * g.K + k)) * g.H + h * 64 + d] = __float2bfloat16_rn(v / t);
+    }
+    nk0 = nk1; nk1 = nk2; nk2 = nk3;
+  }
+}
+
 // cross_len[b] = 1 + index of the last key whose mask is non-zero (Le when the whole row is masked: the reference then
 // spreads uniform weight over every key, which needs them all).
 __global__ void cross_len_kernel(int B, int Le, const float* __restrict__ mask, int* __restrict__ out) {
@@ -237,18 +458,32 @@ bool dec_cross_tma_supported(int dtype, const DecodeGeom& g) {
 
 int launch_dec_cross_tma(const DecodeGeom& g, int layer, const void* q, const void* cross_cache, const float* enc_mask,
                          const int* cross_len, void* out, int num_sms, cudaStream_t stream) {
+  // A/B aid: GSTVD_CROSS_TMA=1 scores through shared memory (first version), =3 one 16-warp CTA per SM with two stages
+  static const int variant = [] { const char* e = getenv("GSTVD_CROSS_TMA"); return e ? atoi(e) : 2; }();
+  using Cfg2 = X2Cfg<8, 1, 3>;
+  using Cfg3 = X2Cfg<16, 2, 2>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(dec_cross_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kXtSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dec_cross_tma2_kernel<8, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::kSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dec_cross_tma2_kernel<16, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg3::kSmem);
     if (e != cudaSuccess) throw std::runtime_error(std::string("dec_cross_tma: ") + cudaGetErrorString(e));
     configured = true;
   }
   const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(
       tma_map_rows3(cross_cache, 64, g.Le, (int64_t)g.layers * g.B * 2 * g.heads, kXtRows));
   const int items = g.B * g.heads;
-  const int grid = items < 2 * num_sms ? items : 2 * num_sms;
-  launch_k(dec_cross_tma_kernel, dim3(grid), dim3(kXtThreads), (size_t)kXtSmem, stream, *tm, g, layer, (const bf16*)q, enc_mask, cross_len,
-           (bf16*)out);
+  const int slots = variant == 3 ? num_sms : 2 * num_sms;
+  const int grid = items < slots ? items : slots;
+  if (variant == 1)
+    launch_k(dec_cross_tma_kernel, dim3(grid), dim3(kXtThreads), (size_t)kXtSmem, stream, *tm, g, layer, (const bf16*)q, enc_mask, cross_len,
+             (bf16*)out);
+  else if (variant == 3)
+    launch_k(dec_cross_tma2_kernel<16, 2, 2>, dim3(grid), dim3(Cfg3::kThreads), (size_t)Cfg3::kSmem, stream, *tm, g, layer, (const bf16*)q,
+             enc_mask, cross_len, (bf16*)out);
+  else
+    launch_k(dec_cross_tma2_kernel<8, 1, 3>, dim3(grid), dim3(Cfg2::kThreads), (size_t)Cfg2::kSmem, stream, *tm, g, layer, (const bf16*)q,
+             enc_mask, cross_len, (bf16*)out);
   return 1;
 }
 

@@ -281,6 +281,36 @@ def test_full_bf16_vs_fp32(full_engines, full_cfgs, golden_dir):
     assert s16.shape == (3, 18)
 
 
+@pytest.mark.parametrize("hist", [256, 140])
+def test_full_cached_decode_agrees_with_teacher_forced_pass(full_engines, full_cfgs, hist):
+    """KV-cached decode steps (decode-step attention kernels over the self / cross caches, Le up to 293) against the
+    teacher-forced pass over the same tokens (different kernels, same weights): the argmax of the teacher-forced logits
+    reproduces the greedy tokens.  Full-length histories exercise every key group / TMA box of the cross-attention."""
+    e32, e16 = full_engines
+    enc_cfg = full_cfgs[0]
+    B = 3
+    b = history_batch(enc_cfg, 0, B)
+    g = torch.Generator().manual_seed(hist)
+    ids = b["enc_input_ids"]
+    for i in range(B):
+        n = int((ids[i] != 0).sum())
+        ids[i, n:hist] = torch.randint(1000, enc_cfg.vocab_size, (hist - n,), generator=g)
+    b["enc_att_mask"] = (ids != 0).float()
+    for e, need in ((e32, 0.98), (e16, 0.75)):           # bf16: near-tied logits of a random-weight model may flip the argmax
+        o = e.encode(ids, b["enc_image_feat"], b["enc_image_loc"], b["enc_segments"], b["enc_att_mask"], b["enc_image_mask"])
+        e.prefill_cross(B, o["Le"])
+        out = e.generate(B, num_beams=1, top_k=1)
+        dec_in = torch.cat((torch.full((B, 1), 101, dtype=torch.int64, device=out.device), out[:, :-1]), 1).contiguous()
+        _, lg = e.score(dec_in, None, labels=torch.zeros_like(dec_in), want_logits=True)
+        assert torch.isfinite(lg).all()
+        agree = (lg.argmax(-1) == out).float().mean().item()
+        top3 = (lg.topk(3, -1).indices == out.unsqueeze(-1)).any(-1).float().mean().item()
+        assert top3 >= 0.95, f"generated tokens inside the teacher-forced top-3 at only {top3:.3f} of the positions"
+        beam = e.generate(B, num_beams=5)
+        assert agree >= need, f"{e.dtype}: cached decode vs teacher-forced argmax agreement {agree:.3f}"
+        assert ((beam >= 0) & (beam < enc_cfg.vocab_size)).all()
+
+
 # ---- the ten-round loop of generate.py:122-233 (SURVEY.md row a17) ------------------------------------------------------
 def test_dialog_loop_matches_reference_loop(tiny_cfgs, tiny_sd):
     """Questioner + teacher alternating rounds with history splices and the perplexity pass, fp32, greedy with 4-gram
