@@ -382,6 +382,74 @@ __device__ __forceinline__ void epilogue_tma_block(const GemmArgs& p, const CUte
   }
 }
 
+// Epilogue of one 32-column block straight from registers: thread = accumulator row, 64 (bf16) or 128 (fp32) contiguous
+// bytes per row as 16-byte stores.  Uncoalesced across the warp, which costs L2 transactions on big outputs (that is why
+// the throughput configurations stage through shared memory + TMA), but for the skinny decode GEMMs the whole tile is 8 KB
+// and what matters is latency: no staging tile, no proxy fence, no group barrier, no wait for the TMA engine at the end.
+template <typename OutT>
+__device__ __forceinline__ void epilogue_direct_block(const GemmArgs& p, uint32_t taddr, int row, int col0, const float* bpre) {
+  constexpr int kWords = 32 * (int)sizeof(OutT) / 4;
+  uint32_t acc[32];
+  tmem_ld32(taddr, acc);
+  uint32_t packed[kWords];
+  const bool full = (col0 + 32 <= p.N);
+  const bool bias_vec = p.bias != nullptr && full && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0);
+#pragma unroll
+  for (int g8 = 0; g8 < 4; ++g8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g8 * 8 + j]);
+    const int cb = col0 + g8 * 8;
+    if (bpre != nullptr) {                               // bias values fetched while the main loop was running
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += bpre[g8 * 8 + j];
+    } else if (p.bias) {
+      if (bias_vec) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cb));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + 4));
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (cb + j < p.N) v[j] += __ldg(p.bias + cb + j);
+      }
+    }
+    if (p.act == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = gelu_fast(v[j]);
+    }
+    if constexpr (sizeof(OutT) == 2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        packed[g8 * 4 + j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) packed[g8 * 8 + j] = __float_as_uint(v[j]);
+    }
+  }
+  if (row >= p.M || p.dbg == 1) return;
+  OutT* dst = reinterpret_cast<OutT*>(p.C) + (int64_t)row * p.ldc + col0;
+  if (full) {                                            // launch_cfg guarantees 16-byte aligned rows in this mode
+#pragma unroll
+    for (int c = 0; c < kWords / 4; ++c)
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(dst) + 4 * c) = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (col0 + j < p.N) {
+        if constexpr (sizeof(OutT) == 2) {
+          const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&packed[j >> 1]);
+          dst[j] = (j & 1) ? h.y : h.x;
+        } else {
+          dst[j] = __uint_as_float(packed[j]);
+        }
+      }
+    }
+  }
+}
+
 template <int BN, int EW>
 __global__ void __launch_bounds__((2 + EW) * 32, EW == kEpiWarpsSkinny ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -418,7 +486,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
-    if (p.tma_store) tma_prefetch_desc(&tm_c);
+    if (p.tma_store == 1) tma_prefetch_desc(&tm_c);
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EW * 32); }
     fence_barrier_init();
@@ -526,13 +594,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const int c0 = n_blk * BN + (e & 7) * (BN / 8);
         if (c0 < p.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + c0));
       }
+      // direct-store (decode) mode: the bias of this warp's first column block is fetched now, under the main loop
+      float bpre[32];
+      bool have_bpre = false;
+      if (p.tma_store == 2 && p.bias != nullptr && grp < BN / 32) {
+        const int c0 = n_blk * BN + grp * 32;
+        if (c0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(p.bias + c0) & 15) == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + j);
+            bpre[4 * j] = b4.x; bpre[4 * j + 1] = b4.y; bpre[4 * j + 2] = b4.z; bpre[4 * j + 3] = b4.w;
+          }
+          have_bpre = true;
+        }
+      }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       if (stamps && e == 0 && lane == 0) stamps[5] = global_ns();
       const int row0 = m_blk * BM + quad * 32;
       if (p.dbg == 2) { tc_fence_before(); mbar_arrive(tempty_bar(as)); continue; }
       constexpr int kWb = (BN >= 128) ? 64 : 32;           // block width of the generic (non-TMA) bf16 path
-      if (p.tma_store) {
+      if (p.tma_store == 2) {
+        const uint32_t tq = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+        for (int j = grp; j < BN / 32; j += kGroups) {
+          const int col0 = n_blk * BN + j * 32;
+          if (col0 >= p.N) break;
+          const float* bp = (have_bpre && j == grp) ? bpre : nullptr;
+          if (p.out_f32) epilogue_direct_block<float>(p, tq + j * 32, row0 + lane, col0, bp);
+          else epilogue_direct_block<bf16>(p, tq + j * 32, row0 + lane, col0, bp);
+        }
+      } else if (p.tma_store) {
         const int r = quad * 32 + lane;                     // accumulator row == TMEM lane == staging row
         const bool issuer = (e & 3) == 0 && lane == 0;
         const uint32_t tq = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
@@ -574,7 +665,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
     // the staging tiles must have been read before the CTA's shared memory goes away; the global writes themselves are
     // complete (and visible to the next kernel) at grid end like any other store
-    if (p.tma_store && (e & 3) == 0 && lane == 0) bulk_wait_read0();
+    if (p.tma_store == 1 && (e & 3) == 0 && lane == 0) bulk_wait_read0();
     if (stamps && e == 0 && lane == 0) stamps[6] = global_ns();
   }
   tc_fence_before();
@@ -711,8 +802,13 @@ void launch_cfg(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
         a.tma_store = 1;
       }
     } else if ((a.ldc * esz) % 16 == 0) {
-      mc = &get_map_c(a.C, a.M, a.N, a.ldc, esz, cw);
-      a.tma_store = 1;
+      static const bool no_direct = getenv("GSTVD_GEMM_NO_DIRECT") != nullptr;     // A/B aid
+      if (a.M <= 4 * BM && (int64_t)a.M * a.N * esz <= (4 << 20) && !no_direct) {
+        a.tma_store = 2;                                 // skinny (decode) problems: latency matters, the tile is tiny
+      } else {
+        mc = &get_map_c(a.C, a.M, a.N, a.ldc, esz, cw);
+        a.tma_store = 1;
+      }
     }
   }
   const int tiles_m = a.hm_tpi > 0 ? a.hm_B * a.hm_tpi : (a.M + BM - 1) / BM;
