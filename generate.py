@@ -26,6 +26,7 @@ from gst_visdial_b200 import options  # noqa: E402
 from gst_visdial_b200 import synthetic as S  # noqa: E402
 from gst_visdial_b200 import weights as W  # noqa: E402
 from gst_visdial_b200.dialog import generate_dialogs  # noqa: E402
+from gst_visdial_b200.io import output as IOO  # noqa: E402
 from gst_visdial_b200.models.visual_dialog_decoder import VisualDialogDecoder  # noqa: E402
 from gst_visdial_b200.models.visual_dialog_encoder import VisualDialogEncoder  # noqa: E402
 from gst_visdial_b200.models.visual_dialog_model import EncoderDecoderModel  # noqa: E402
@@ -60,41 +61,65 @@ def main(argv=None):
         params['gpu_ids'] = [local]
         params['device'] = f"cuda:{local}"
     torch.cuda.set_device(params['device'])
-    if params['synthetic'] <= 0:
-        raise SystemExit("the LMDB / tokenizer data path of the reference is host I/O outside this package; run with -synthetic N "
-                         "or feed gst_visdial_b200.dialog.generate_dialogs() with batches from the reference's CC12mDataset")
+    shards = None
+    if params['feature_shards']:
+        from gst_visdial_b200.io import features as IOF
+        shards = IOF.FeatureShards([d for d in params['feature_shards'].split(',') if d])
+        captions = {int(k): v for k, v in json.load(open(params['caption_ids'])).items()} if params['caption_ids'] else {}
+        all_ids = sorted(shards.image_ids())
+    elif params['synthetic'] <= 0:
+        raise SystemExit("give -feature_shards DIR[,DIR] (+ -caption_ids) or -synthetic N; the reference's LMDB / tokenizer readers are "
+                         "host I/O outside this package (convert an LMDB once with gst_visdial_b200.io.features)")
     q_model = build_model(params, 'enc_dec_q', params['start_path_q'], seed=7)
     a_model = build_model(params, 'enc_dec_a', params['start_path_a'], seed=0)
     enc_cfg = a_model.module.encoder.config
-    total = params['synthetic']
+    total = len(all_ids) if shards is not None else params['synthetic']
     start, end = D.shard_range(total, rank, world)
     a_kwargs = dict(temperature=0.7, top_k=7, top_p=0.0, ngram_blocking_size=0)
     if params['num_beams'] > 1:
         a_kwargs.update(num_beams=params['num_beams'])
     q_kwargs = dict(temperature=0.7, top_k=7, top_p=0.0, ngram_blocking_size=4)
-    out = []
-    with torch.no_grad():
-        for s in range(start, end, params['batch_size']):
-            n = min(params['batch_size'], end - s)
-            batch = S.synthetic_batch(s, n, vocab_size=enc_cfg.vocab_size, v_feature_size=enc_cfg.v_feature_size,
-                                      max_seq_len=params['max_seq_len'])
+    decode = None
+    if params['vocab_file']:
+        from transformers import BertTokenizer
+        tok = BertTokenizer(params['vocab_file'])
+        decode = lambda ids: tok.decode(ids, skip_special_tokens=True)      # noqa: E731  (generate.py:18-23)
+    bs = params['batch_size']
+    spans = [(s, min(bs, end - s)) for s in range(start, end, bs)]
+
+    def batches():
+        if shards is None:
+            for s, n in spans:
+                yield S.synthetic_batch(s, n, vocab_size=enc_cfg.vocab_size, v_feature_size=enc_cfg.v_feature_size, max_seq_len=params['max_seq_len'])
+        else:
+            id_batches = [all_ids[s:s + n] for s, n in spans]
+            for ids, fb in zip(id_batches, IOF.Prefetcher(shards, id_batches, depth=2)):
+                fb.update(IOF.caption_batch([captions.get(i, []) for i in ids], max_seq_len=params['max_seq_len']))
+                yield fb
+
+    # every finished batch is appended to this rank's JSON-lines file by a writer thread (gst_visdial_b200/io/output.py)
+    final = os.path.join(params['save_path'], params['save_name'])
+    part = f"{final}.rank{rank}.jsonl"
+    with torch.no_grad(), IOO.JsonlWriter(part) as writer:
+        for batch in batches():
             res = generate_dialogs(a_model, batch, q_model=q_model, num_rounds=params['num_rounds'], a_kwargs=a_kwargs, q_kwargs=q_kwargs,
                                    with_ppl=True, device=params['device'])
-            q, a, ppl, abn = res.questions.cpu(), res.answers.cpu(), res.answer_ppl.cpu(), res.abnormal.cpu()
-            for j in range(n):
-                if abn[j]:
-                    continue                                                          # generate.py:236-237
-                out.append({"image_id": int(batch["image_id"][j]), "url": "", "caption": ids_to_text(batch["enc_input_ids"][j]),
-                            "dialog": [{"question": ids_to_text(q[j, k]), "answer": ids_to_text(a[j, k]),
-                                        "answer_ppl": float(ppl[j, k])} for k in range(params['num_rounds'])]})
+            meta = {int(i): {"url": "", "caption": (decode or ids_to_text)(IOO.strip_ids(row) if decode else row)}
+                    for i, row in zip(batch["image_id"].tolist(), batch["enc_input_ids"].tolist())}
+            writer.write(IOO.batch_records(batch["image_id"], res.questions, res.answers, res.answer_ppl, res.abnormal,
+                                           decode=decode or ids_to_text, meta=meta))
     if world > 1:
-        gathered = [None] * world
-        torch.distributed.all_gather_object(gathered, out)
-        out = [d for part in gathered for d in part]
+        torch.distributed.barrier()
     if rank == 0:
-        path = os.path.join(params['save_path'], params['save_name'])
-        json.dump(out, open(path, "w"))
-        print(f"wrote {len(out)} dialogs to {path}")
+        merged = f"{final}.jsonl"
+        with open(merged, "w") as dst:
+            for r in range(world):
+                with open(f"{final}.rank{r}.jsonl") as src:
+                    for line in src:
+                        dst.write(line)
+                os.remove(f"{final}.rank{r}.jsonl")
+        n = IOO.jsonl_to_reference_json(merged, final)                     # the reference's single-array file (generate.py:258)
+        print(f"wrote {n} dialogs to {final} (streamed copy: {merged})")
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -55,7 +55,8 @@ def generate_dialogs(a_model, batch, q_model=None, questions=None, num_rounds=10
     eng = am._engine(dev)
     nb = dict(device=dev, non_blocking=True)
     st = {
-        "feat": batch["enc_image_feat"].to(dtype=torch.float32, **nb), "loc": batch["enc_image_loc"].to(dtype=torch.float32, **nb),
+        # features travel in their own dtype (bf16 shards: 152 KB / image) and are widened on the device
+        "feat": batch["enc_image_feat"].to(**nb).to(torch.float32), "loc": batch["enc_image_loc"].to(dtype=torch.float32, **nb),
         "imask": batch["enc_image_mask"].to(dtype=torch.float32, **nb),
         "ids": batch["enc_input_ids"].to(dtype=torch.int64, **nb).clone().contiguous(),
         "seg": batch["enc_segments"].to(dtype=torch.int64, **nb).clone().contiguous(),

@@ -35,6 +35,9 @@ def read_command_line(argv=None):
     p.add_argument('-compute_dtype', default='bf16', choices=['bf16', 'fp32'], help='arithmetic of the CUDA engine')
     p.add_argument('-num_beams', default=1, type=int, help='>1: beam search for the answers instead of top-k sampling')
     p.add_argument('-synthetic', default=0, type=int, help='generate dialogs for N seeded synthetic images (no dataset / checkpoint needed)')
+    p.add_argument('-feature_shards', default='', help='comma-separated shard directories (gst_visdial_b200.io.features) instead of the LMDB')
+    p.add_argument('-caption_ids', default='', help='json {image_id: [caption token ids]} for the images of the shards (pre-tokenized captions)')
+    p.add_argument('-vocab_file', default='', help='optional BERT vocab.txt: decode the generated ids to text in the output')
     p.add_argument('-num_rounds', default=10, type=int)
     p.add_argument('-seed', default=0, type=int)
     args = p.parse_args(argv)

@@ -388,6 +388,32 @@ def test_generate_cli_synthetic(tmp_path):
     assert len(out) == 5 and len(out[0]["dialog"]) == 2 and out[0]["dialog"][0]["answer_ppl"] > 0
 
 
+def test_generate_cli_feature_shards(tmp_path, tiny_cfgs):
+    """generate.py fed from bf16 feature shards + pre-tokenized captions, streamed JSONL output (f4)."""
+    import json
+    import subprocess
+    import sys
+    from gst_visdial_b200 import synthetic as S, weights as W
+    from gst_visdial_b200.io import features as IOF
+    from helpers import ROOT
+    enc_cfg, _ = tiny_cfgs
+    b = S.synthetic_batch(0, 6, vocab_size=enc_cfg.vocab_size, v_feature_size=enc_cfg.v_feature_size)
+    ids = [500 + i for i in range(6)]
+    IOF.write_shard(str(tmp_path / "s0"), ids[:4], b["enc_image_feat"][:4].numpy(), b["enc_image_loc"][:4].numpy(), b["enc_image_mask"][:4].numpy())
+    IOF.write_shard(str(tmp_path / "s1"), ids[4:], b["enc_image_feat"][4:].numpy(), b["enc_image_loc"][4:].numpy(), b["enc_image_mask"][4:].numpy())
+    caps = {str(i): [int(t) for t in row[1:] if int(t) not in (0, 102)] for i, row in zip(ids, b["enc_input_ids"].tolist())}
+    json.dump(caps, open(tmp_path / "caps.json", "w"))
+    cmd = [sys.executable, os.path.join(ROOT, "generate.py"), "-feature_shards", f"{tmp_path / 's0'},{tmp_path / 's1'}", "-caption_ids",
+           str(tmp_path / "caps.json"), "-batch_size", "4", "-num_rounds", "2", "-model_enc_config", W.TINY_ENC_CONFIG, "-model_dec_config",
+           W.TINY_DEC_CONFIG, "-save_path", str(tmp_path), "-save_name", "o.json", "-compute_dtype", "bf16"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = json.load(open(tmp_path / "o.json"))
+    assert [d["image_id"] for d in out] == ids and len(out[0]["dialog"]) == 2
+    assert out[2]["caption"] == " ".join(str(t) for t in [101] + caps["502"] + [102])
+    assert sum(1 for _ in open(tmp_path / "o.json.jsonl")) == 6
+
+
 def test_generative_ranking_shares_encoder(tiny_fp32, tiny_cfgs, tiny_sd):
     """f1 (evaluate_gen.py:62-107): O options per image scored against one encoder pass == scoring every option separately."""
     from gst_visdial_b200.ranking import score_options
