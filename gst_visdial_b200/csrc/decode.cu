@@ -44,7 +44,7 @@ template <> struct Raw16<float> {
 template <typename T, int ND>
 __global__ void __launch_bounds__(128)
 dec_self_attn_kernel(DecodeGeom g, int layer, const T* __restrict__ qkv, T* __restrict__ cache, const int* __restrict__ d_step,
-                     const int* __restrict__ anc, T* __restrict__ out) {
+                     T* __restrict__ out) {
   constexpr int EPL = 16 / sizeof(T);
   __shared__ __align__(16) float qs[4][128];
   pdl_wait();
@@ -67,15 +67,12 @@ dec_self_attn_kernel(DecodeGeom g, int layer, const T* __restrict__ qkv, T* __re
       qs[warp][d] = q[u];
     } else { q[u] = kn[u] = vn[u] = 0.f; }
   }
-  // cache row of (kv, position t) in beam slot `slot` for this image/head.  With an ancestry table (beam search) the
-  // history of beam kb is not physically gathered after every step: position t of its history lives in slot anc[b][kb][t]
-  // (the beam that wrote it), and only the 32-entry table row is permuted per step (anc_update_kernel).
-  auto cache_ptr = [&](int kv, int t, int slot) -> T* {
-    return cache + (((((int64_t)layer * 2 + kv) * g.B + b) * g.T + t) * g.K + slot) * H + h * D;
+  // cache row of (kv, position t) for this beam/head
+  auto cache_ptr = [&](int kv, int t) -> T* {
+    return cache + (((((int64_t)layer * 2 + kv) * g.B + b) * g.T + t) * g.K + kb) * H + h * D;
   };
-  const int my_slot = (anc != nullptr && lane < step) ? anc[((int64_t)b * g.K + kb) * kMaxSteps + lane] : kb;   // lane t <-> position t
   {
-    T* kc = cache_ptr(0, step, kb); T* vc = cache_ptr(1, step, kb);
+    T* kc = cache_ptr(0, step); T* vc = cache_ptr(1, step);
 #pragma unroll
     for (int u = 0; u < 4; ++u)
       if (u < nd) { kc[lane + 32 * u] = from_f32<T>(kn[u]); vc[lane + 32 * u] = from_f32<T>(vn[u]); }
@@ -87,8 +84,7 @@ dec_self_attn_kernel(DecodeGeom g, int layer, const T* __restrict__ qkv, T* __re
 #pragma unroll
     for (int i = 0; i < VB; ++i) {
       const int t = t0 + i;
-      const int slot = __shfl_sync(0xffffffffu, my_slot, t & 31);
-      const T* vc = cache_ptr(1, t < step ? t : 0, t < step ? slot : kb);
+      const T* vc = cache_ptr(1, t < step ? t : 0);
 #pragma unroll
       for (int u = 0; u < ND; ++u) vv[i][u] = (t < step) ? to_f32(vc[lane + 32 * u]) : 0.f;
     }
@@ -103,7 +99,7 @@ dec_self_attn_kernel(DecodeGeom g, int layer, const T* __restrict__ qkv, T* __re
   // scores of the cached positions: lane t reads key row t
   float my_score = -INFINITY;
   if (lane < step) {
-    const T* kc = cache_ptr(0, lane, my_slot);
+    const T* kc = cache_ptr(0, lane);
     float dot = 0.f;
     for (int c = 0; c < D / EPL; ++c) {
       float kr[EPL];
@@ -483,25 +479,6 @@ void launch_cross_t(const DecodeGeom& g, const void* q, const void* kv_layer, co
   else launch_cross_kb<T, 8>(g, qq, kv, enc_mask, o, stream);
 }
 
-// Beam reorder without moving the cache: new beam k continues old beam parent = beam_idx[b][k]; its history table row becomes
-// the parent's row, and the position just written (t = step) is found in the parent's slot.  One CTA per image; every
-// entry is read before any is written (parents may repeat).
-__global__ void __launch_bounds__(kMaxBeams * kMaxSteps)
-anc_update_kernel(int B, int K, const int32_t* __restrict__ beam_idx, const int* __restrict__ d_step, int* __restrict__ anc) {
-  pdl_wait();
-  pdl_launch_dependents();
-  const int b = blockIdx.x, k = threadIdx.x / kMaxSteps, t = threadIdx.x % kMaxSteps;
-  const int step = *d_step;
-  int val = 0;
-  const bool live = k < K && t <= step;
-  if (live) {
-    const int parent = beam_idx[b * K + k];
-    val = (t == step) ? parent : anc[((int64_t)b * K + parent) * kMaxSteps + t];
-  }
-  __syncthreads();
-  if (live) anc[((int64_t)b * K + k) * kMaxSteps + t] = val;
-}
-
 // One CTA per (image, layer*2+kv).  Thread-local dependency only: every thread loads the K source values of its
 // column chunk before it stores any of them, so duplicated parents (beam_idx is not a permutation) are safe in place.
 template <typename T>
@@ -538,23 +515,17 @@ reorder_cache_kernel(DecodeGeom g, T* __restrict__ cache, const int32_t* __restr
 
 }  // namespace
 
-int launch_anc_update(const DecodeGeom& g, const int32_t* beam_idx, const int* d_step, int* anc, cudaStream_t stream) {
-  if (g.K > kMaxBeams || g.T > kMaxSteps) throw std::runtime_error("anc_update: at most 8 beams and 32 positions");
-  launch_k(anc_update_kernel, dim3(g.B), dim3(kMaxBeams * kMaxSteps), 0, stream, g.B, g.K, beam_idx, d_step, anc);
-  return 1;
-}
-
 int launch_dec_self_attn(int dtype, const DecodeGeom& g, int layer, const void* qkv, void* self_cache, const int* d_step,
-                         const int* anc, void* out, cudaStream_t stream) {
+                         void* out, cudaStream_t stream) {
   if (g.D != 64 && g.D != 128) throw std::runtime_error("dec_self_attn: head_dim must be 64 or 128");
   if (g.T > kMaxSteps) throw std::runtime_error("dec_self_attn: at most 32 cached positions");
   dim3 grid(g.B * g.K, (g.heads + 3) / 4);
   if (g.D == 64) {
-    if (dtype == kF32) launch_k(dec_self_attn_kernel<float, 2>, grid, dim3(128), 0, stream, g, layer, (const float*)qkv, (float*)self_cache, d_step, anc, (float*)out);
-    else launch_k(dec_self_attn_kernel<bf16, 2>, grid, dim3(128), 0, stream, g, layer, (const bf16*)qkv, (bf16*)self_cache, d_step, anc, (bf16*)out);
+    if (dtype == kF32) launch_k(dec_self_attn_kernel<float, 2>, grid, dim3(128), 0, stream, g, layer, (const float*)qkv, (float*)self_cache, d_step, (float*)out);
+    else launch_k(dec_self_attn_kernel<bf16, 2>, grid, dim3(128), 0, stream, g, layer, (const bf16*)qkv, (bf16*)self_cache, d_step, (bf16*)out);
   } else {
-    if (dtype == kF32) launch_k(dec_self_attn_kernel<float, 4>, grid, dim3(128), 0, stream, g, layer, (const float*)qkv, (float*)self_cache, d_step, anc, (float*)out);
-    else launch_k(dec_self_attn_kernel<bf16, 4>, grid, dim3(128), 0, stream, g, layer, (const bf16*)qkv, (bf16*)self_cache, d_step, anc, (bf16*)out);
+    if (dtype == kF32) launch_k(dec_self_attn_kernel<float, 4>, grid, dim3(128), 0, stream, g, layer, (const float*)qkv, (float*)self_cache, d_step, (float*)out);
+    else launch_k(dec_self_attn_kernel<bf16, 4>, grid, dim3(128), 0, stream, g, layer, (const bf16*)qkv, (bf16*)self_cache, d_step, (bf16*)out);
   }
   return 1;
 }

@@ -101,7 +101,6 @@ struct gstvd_ctx {
   DevBuf dh, da, db, dqkv, dctx, dtmp, dffn, dqc;      // decoder activations, rows = max(B*K, B*Ldec)
   DevBuf logits;                                      // fp32 [rows, Vpad]
   DevBuf cross_cache, self_cache;
-  DevBuf anc;                                         // int32 [B][K][32] beam ancestry of the self-attention cache
   DevBuf cross_len;                                   // int32 [B]: keys up to the last unmasked one (launch_cross_len)
   DevBuf labels;                                      // int64 [B*Ldec]
   DevBuf sel_val, sel_idx, logz;                      // [rows, kSelMax]
@@ -310,7 +309,6 @@ void alloc_workspace(gstvd_ctx* c) {
     A(c->self_cache, (size_t)c->dec_layers * 2 * B * T * K * H);
     c->labels.alloc(B * (size_t)c->Ldec_max * 8);
     c->cross_len.alloc(B * 4);
-    c->anc.alloc(B * K * 32 * 4);
     c->sel_val.alloc(R * kSelMax * 4); c->sel_idx.alloc(R * kSelMax * 4); c->logz.alloc(R * 4);
     c->ban_tokens.alloc(B * Lt * 4); c->ban_count.alloc(B * 4);
     c->prefix.alloc(B * (T + 1) * 4); c->seq.alloc(B * T * 4);
@@ -533,13 +531,12 @@ void decode_step(gstvd_ctx* c, const DecodeGeom& g, const gstvd_gen_params& gp, 
   PdlScope pdl_scope(!(c->cfg.flags & GSTVD_FLAG_NO_PDL));
   const int H = c->H, M = g.B * g.K;
   const int* d_step = (const int*)c->d_step.p;
-  const int* anc = gp.mode == GSTVD_SELECT_BEAM ? (const int*)c->anc.p : nullptr;
   c->launches += launch_embed_step(c->dtype, M, H, (const int32_t*)c->cur_tokens.p, d_step, c->word, c->pos, c->type,
                                    c->emb_ln.g, c->emb_ln.b, c->dh.p, s);
   for (int l = 0; l < c->dec_layers; ++l) {
     const DecLayer& L = c->d_layers[l];
     X.gemm(c->dh.p, H, L.qkv, c->dqkv.p, 3 * H, M);
-    c->launches += launch_dec_self_attn(c->dtype, g, l, c->dqkv.p, c->self_cache.p, d_step, anc, c->dctx.p, s);
+    c->launches += launch_dec_self_attn(c->dtype, g, l, c->dqkv.p, c->self_cache.p, d_step, c->dctx.p, s);
     X.gemm(c->dctx.p, H, L.o, c->dtmp.p, H, M);
     X.add_ln(c->dtmp.p, c->dh.p, L.ln_att, c->da.p, M);
     X.gemm(c->da.p, H, L.cq, c->dqc.p, H, M);
@@ -562,8 +559,7 @@ void decode_step(gstvd_ctx* c, const DecodeGeom& g, const gstvd_gen_params& gp, 
                                      nullptr, 0, nsel, sv, si, nullptr, s);
     BeamBuffers bb = beam_buffers(c);
     c->launches += launch_beam_step(bb, g.B, g.K, g.T, c->V, nsel, sv, si, 102, nullptr, nullptr, nullptr, s);
-    // beam reorder: the self-attention cache stays where it is, its ancestry table is permuted (decode.cu)
-    c->launches += launch_anc_update(g, bb.beam_idx, d_step, (int*)c->anc.p, s);
+    c->launches += launch_reorder_cache(c->dtype, g, c->self_cache.p, bb.beam_idx, d_step, 0, nullptr, s);
   } else {
     const int nsel = kSelMax;
     const int32_t* bt = nullptr; const int32_t* bc = nullptr;
@@ -802,7 +798,7 @@ void gstvd_destroy(gstvd_ctx* c) {
   for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
   DevBuf* bufs[] = {&c->mat32, &c->mat16, &c->vec32, &c->xt, &c->yt, &c->xv, &c->yv, &c->qkv_t, &c->qkv_v, &c->ctx_t, &c->ctx_v, &c->tmp_t,
                     &c->tmp_v, &c->ffn_t, &c->ffn_v, &c->feat_cast, &c->fused, &c->pool, &c->fused_mask, &c->dh, &c->da, &c->db, &c->dqkv,
-                    &c->dctx, &c->dtmp, &c->dffn, &c->dqc, &c->logits, &c->cross_cache, &c->self_cache, &c->cross_len, &c->anc, &c->labels, &c->sel_val, &c->sel_idx,
+                    &c->dctx, &c->dtmp, &c->dffn, &c->dqc, &c->logits, &c->cross_cache, &c->self_cache, &c->cross_len, &c->labels, &c->sel_val, &c->sel_idx,
                     &c->logz, &c->ban_tokens, &c->ban_count, &c->prefix, &c->seq, &c->beam_scores, &c->beam_tokens, &c->cur_tokens,
                     &c->beam_idx, &c->beam_done, &c->hyp_score, &c->hyp_len, &c->hyp_tokens, &c->hyp_count, &c->hyp_worst, &c->d_step, &c->d_seed};
   for (DevBuf* b : bufs) b->release();

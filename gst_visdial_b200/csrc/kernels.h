@@ -109,11 +109,8 @@ struct DecodeGeom {
 };
 // self-attention for one new position per row: appends k/v at position *d_step and attends over 0..*d_step
 // qkv [M, 3H]; cache layout [layer][kv][b][t][k][H]
-// anc (nullable): ancestry table int32 [B][K][32] - position t of beam k's history lives in beam slot anc[b][k][t]
 int launch_dec_self_attn(int dtype, const DecodeGeom& g, int layer, const void* qkv, void* self_cache, const int* d_step,
-                         const int* anc, void* out, cudaStream_t stream);
-// beam reorder as a permutation of the ancestry table rows (instead of launch_reorder_cache moving the cache)
-int launch_anc_update(const DecodeGeom& g, const int32_t* beam_idx, const int* d_step, int* anc, cudaStream_t stream);
+                         void* out, cudaStream_t stream);
 // cross-attention of every beam row over its image's cross K/V. cross layout [layer][b][kv*heads+h][Le][D]
 int launch_dec_cross_attn(int dtype, const DecodeGeom& g, int layer, const void* q, const void* cross_cache,
                           const float* enc_mask, void* out, cudaStream_t stream);
