@@ -113,6 +113,7 @@ struct gstvd_ctx {
   int op_B = 0, op_K = 0, op_T = 0;
 
   std::map<GraphKey, cudaGraphExec_t> graphs;
+  std::map<GraphKey, int64_t> graph_kernels;          // kernels per replay, counted while the step was captured
   // optional event profiling of the tcgen05 GEMM launches (bench.py roofline): one event pair per launch
   bool profiling = false; int prof_min_rows = 0;
   struct ProfRec { cudaEvent_t a, b; double flops, bytes; };
@@ -629,14 +630,10 @@ void do_generate(gstvd_ctx* c, int B, const gstvd_gen_params& gp, const int64_t*
       CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
       CUDA_CHECK(cudaGraphDestroy(graph));
       it = c->graphs.emplace(key, exec).first;
-      c->launches = before;                       // capture launches nothing
+      c->graph_kernels[key] = c->launches - before;   // kernels per replay = what the captured step enqueued
+      c->launches = before;                           // capture itself launches nothing
     }
-    // kernels per replay = what one eager step would have launched
-    int64_t per_step;
-    {
-      const int per_layer = 11;
-      per_step = 1 + (int64_t)c->dec_layers * per_layer + 1 + (gp.mode == GSTVD_SELECT_BEAM ? 3 : (gp.ngram_blocking_size > 0 ? 3 : 2)) + 1;
-    }
+    const int64_t per_step = c->graph_kernels[key];
     for (int t = 0; t < T; ++t) { CUDA_CHECK(cudaGraphLaunch(it->second, s)); c->launches += per_step; }
   }
   if (gp.mode == GSTVD_SELECT_BEAM) c->launches += launch_beam_finalize(beam_buffers(c), B, K, T, 102, out_ids, out_scores, s);

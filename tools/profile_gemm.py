@@ -15,7 +15,10 @@ from gst_visdial_b200.engine import Engine  # noqa: E402
 
 shapes = [(16384, 2304, 768, 0), (16384, 3072, 768, 1), (16384, 768, 3072, 0), (16384, 768, 768, 0), (18752, 18432, 768, 0),
           (2368, 3072, 1024, 0), (320, 2304, 768, 0), (320, 768, 768, 0), (320, 3072, 768, 1), (320, 768, 3072, 0), (320, 30522, 768, 0)]
-if len(sys.argv) > 1:
+if len(sys.argv) > 1 and sys.argv[1] == "sweep":      # text-stream shapes at trimmed history lengths (B = 64, Lt = 32 .. 256)
+    shapes = [(64 * lt, n, k, act) for lt in (32, 64, 128, 192, 256) for (n, k, act) in ((2304, 768, 0), (768, 768, 0), (3072, 768, 1), (768, 3072, 0))]
+    shapes += [(2368, 1024, 1024, 0), (2368, 3072, 1024, 0), (2368, 1024, 2048, 0)]
+elif len(sys.argv) > 1:
     shapes = shapes[: int(sys.argv[1])]
 reps = int(os.environ.get("REPS", "20"))
 eng = Engine(W.load_json_config(W.TINY_ENC_CONFIG), W.load_json_config(W.TINY_DEC_CONFIG), dtype="bf16", max_batch=2)
