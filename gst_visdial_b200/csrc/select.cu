@@ -223,9 +223,9 @@ row_select_cluster_kernel(int V, const float* __restrict__ logits, int64_t ldl, 
     double acc = 0.0;
     if (m > -INFINITY) {
       const double md = (double)m;
+      // no bounds test per slot: slots past the vocabulary hold -inf and add exp(-700) ~ 1e-304, i.e. nothing
 #pragma unroll
-      for (int s = 0; s < kRsSlots; ++s)
-        if (base + tid + s * kRsThreads < V) acc += exp_nonpos((double)v[s] - md);
+      for (int s = 0; s < kRsSlots; ++s) acc += exp_nonpos((double)v[s] - md);
     }
     acc = warp_sum(acc);
     if (lane == 0) s_d[warp] = acc;
