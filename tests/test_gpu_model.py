@@ -494,3 +494,73 @@ def test_nsp_rank_config5(tiny_cfgs, tiny_sd):
         ref = torch.softmax(R.nsp_scores(tiny_sd, t, v), 1)[:, 0]
     assert max_abs(p, ref) < 1e-3
     assert torch.equal(p.argsort(descending=True), ref.argsort(descending=True))
+
+
+# ---- edges and error behaviour ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,K", [(1, 8), (4, 1), (2, 2)])
+def test_tiny_fp32_beam_widths_match_oracle(tiny_cfgs, tiny_sd, B, K):
+    """Smallest batch with the widest beam the kernels support (8); beam 1 (served by the greedy path: same tokens); beam 2."""
+    from gst_visdial_b200.engine import Engine
+    enc_cfg, dec_cfg = tiny_cfgs
+    e = Engine(enc_cfg, dec_cfg, dtype="fp32", max_batch=B, max_beams=K)
+    e.load_state_dict(tiny_sd)
+    b = history_batch(enc_cfg, 10, B)
+    with torch.no_grad():
+        ref_seq, ref_sc = OB.beam_search(tiny_sd, enc_cfg, dec_cfg, b, num_beams=K)
+    o = e.encode(b["enc_input_ids"], b["enc_image_feat"], b["enc_image_loc"], b["enc_segments"], b["enc_att_mask"], b["enc_image_mask"])
+    e.prefill_cross(B, o["Le"])
+    seq, sc = e.generate(B, num_beams=K, want_scores=True)
+    assert torch.equal(seq.cpu(), ref_seq)
+    if K > 1:                                             # num_beams = 1 takes the greedy path, which keeps no hypothesis scores
+        assert torch.allclose(sc.cpu().double(), ref_sc, atol=1e-4)
+    e.close()
+
+
+def test_capacity_and_state_errors_are_reported(tiny_cfgs, tiny_sd):
+    """The C ABI reports misuse through status codes + gstvd_last_error (raised as GstvdError), it never writes out of bounds."""
+    from gst_visdial_b200._lib import GstvdError
+    from gst_visdial_b200.engine import Engine
+    enc_cfg, dec_cfg = tiny_cfgs
+    e = Engine(enc_cfg, dec_cfg, dtype="bf16", max_batch=2, max_beams=2)
+    b = history_batch(enc_cfg, 0, 3)
+    args = (b["enc_input_ids"], b["enc_image_feat"], b["enc_image_loc"], b["enc_segments"], b["enc_att_mask"], b["enc_image_mask"])
+    with pytest.raises(GstvdError):                       # weights not loaded yet
+        e.encode(*[a[:2] for a in args])
+    e.load_state_dict(tiny_sd)
+    with pytest.raises(GstvdError, match="capacity"):     # 3 images into a context sized for 2
+        e.encode(*args)
+    with pytest.raises(GstvdError):                       # nothing prefilled yet
+        e.generate(2, num_beams=2)
+    o = e.encode(*[a[:2] for a in args])
+    e.prefill_cross(2, o["Le"])
+    with pytest.raises(GstvdError, match="num_beams"):    # wider than the context was built for
+        e.generate(2, num_beams=5)
+    with pytest.raises(GstvdError):                       # prefilled for 2 images, asked for 1
+        e.generate(1, num_beams=2)
+    with pytest.raises(GstvdError):                       # top_k = 0 (pure nucleus) is documented as unsupported
+        e.generate(2, num_beams=1, top_k=0, top_p=0.9, temperature=1.0)
+    ids = e.generate(2, num_beams=2)                      # and the context still works afterwards
+    assert ids.shape == (2, 18)
+    e.close()
+
+
+def test_score_max_length_and_single_token(tiny_fp32, tiny_cfgs, tiny_sd):
+    """Teacher-forced pass at the longest decoder input the context accepts (max_utt_len = 25) and at length 1."""
+    model, _ = tiny_fp32
+    enc_cfg, dec_cfg = tiny_cfgs
+    B = 2
+    b = history_batch(enc_cfg, 0, B)
+    eng = model.module._engine(torch.device("cuda:0"))
+    o = eng.encode(b["enc_input_ids"], b["enc_image_feat"], b["enc_image_loc"], b["enc_segments"], b["enc_att_mask"], b["enc_image_mask"])
+    eng.prefill_cross(B, o["Le"])
+    with torch.no_grad():
+        t, v = R.encoder(tiny_sd, enc_cfg, b["enc_input_ids"], b["enc_image_feat"], b["enc_image_loc"], b["enc_segments"], b["enc_att_mask"], b["enc_image_mask"])
+        eh, em = R.vlfusion(tiny_sd, t, v, b["enc_att_mask"], b["enc_image_mask"])
+    g = torch.Generator().manual_seed(9)
+    for L in (25, 1):
+        ids = torch.randint(104, enc_cfg.vocab_size, (B, L), generator=g)
+        ids[:, 0] = 101
+        _, lg = eng.score(ids.cuda(), None, labels=torch.zeros(B, L, dtype=torch.int64).cuda(), want_logits=True)
+        with torch.no_grad():
+            ref = R.lm_logits(tiny_sd, R.decoder_hidden(tiny_sd, dec_cfg, ids, torch.ones(B, L), eh, em))
+        assert max_abs(lg.cpu(), ref) < FP32_LOGIT_TOL
