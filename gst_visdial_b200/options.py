@@ -38,6 +38,7 @@ def read_command_line(argv=None):
     p.add_argument('-feature_shards', default='', help='comma-separated shard directories (gst_visdial_b200.io.features) instead of the LMDB')
     p.add_argument('-caption_ids', default='', help='json {image_id: [caption token ids]} for the images of the shards (pre-tokenized captions)')
     p.add_argument('-vocab_file', default='', help='optional BERT vocab.txt: decode the generated ids to text in the output')
+    p.add_argument('-num_options', default=100, type=int, help='answer options per round (evaluate_gen.py)')
     p.add_argument('-num_rounds', default=10, type=int)
     p.add_argument('-seed', default=0, type=int)
     args = p.parse_args(argv)

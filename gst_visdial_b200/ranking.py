@@ -71,3 +71,21 @@ def nsp_rank(encoder, item, device=None) -> torch.Tensor:
     out = encoder(item["tokens"].to(dev), item["image_feat"].to(dev), item["image_loc"].to(dev), token_type_ids=item["segments"].to(dev),
                   attention_mask=item["mask"].to(dev), image_attention_mask=item["image_mask"].to(dev))
     return torch.softmax(out[3].float(), dim=1)[:, 0]
+
+
+def scores_to_ranks(scores: torch.Tensor) -> torch.Tensor:
+    """[B, R, O] option scores -> 1-based ranks, the largest score gets rank 1 (utils/visdial_metrics.py:21-39, vectorised:
+    the reference fills ``ranks[i][ranked_idx[i][j]] = j`` in two Python loops; a scatter of arange does the same)."""
+    B, R, O = scores.shape
+    flat = scores.reshape(-1, O)
+    ranked_idx = flat.sort(1, descending=True).indices
+    ranks = torch.empty_like(ranked_idx)
+    ranks.scatter_(1, ranked_idx, torch.arange(O, device=flat.device).expand_as(ranked_idx))
+    return (ranks + 1).reshape(B, R, O)
+
+
+def sparse_metrics(gt_ranks: torch.Tensor) -> dict:
+    """Recall@{1,5,10}, mean rank and mean reciprocal rank of the ground-truth option (utils/visdial_metrics.py:79-95)."""
+    r = gt_ranks.reshape(-1).float()
+    return {"r@1": (r <= 1).float().mean().item(), "r@5": (r <= 5).float().mean().item(), "r@10": (r <= 10).float().mean().item(),
+            "mean": r.mean().item(), "mrr": r.reciprocal().mean().item()}

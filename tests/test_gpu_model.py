@@ -564,3 +564,21 @@ def test_score_max_length_and_single_token(tiny_fp32, tiny_cfgs, tiny_sd):
         with torch.no_grad():
             ref = R.lm_logits(tiny_sd, R.decoder_hidden(tiny_sd, dec_cfg, ids, torch.ones(B, L), eh, em))
         assert max_abs(lg.cpu(), ref) < FP32_LOGIT_TOL
+
+
+def test_evaluate_gen_cli_synthetic(tmp_path):
+    """evaluate_gen.py end to end on the tiny configs: ranks json in the reference's layout + sparse metrics."""
+    import json
+    import subprocess
+    import sys
+    from gst_visdial_b200 import weights as W
+    from helpers import ROOT
+    cmd = [sys.executable, os.path.join(ROOT, "evaluate_gen.py"), "-synthetic", "3", "-num_options", "7", "-num_rounds", "2", "-batch_size", "14",
+           "-model_enc_config", W.TINY_ENC_CONFIG, "-model_dec_config", W.TINY_DEC_CONFIG, "-save_path", str(tmp_path), "-save_name", "r.json",
+           "-compute_dtype", "fp32"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = json.load(open(tmp_path / "r.json"))
+    assert len(out) == 6 and sorted(out[0]["ranks"]) == list(range(1, 8)) and {d["round_id"] for d in out} == {1, 2}
+    m = json.loads(r.stdout.strip().splitlines()[-1])
+    assert 0.0 <= m["mrr"] <= 1.0 and 1.0 <= m["mean"] <= 7.0
