@@ -156,27 +156,32 @@ constexpr int kRsCandCap = 128;       // candidates (elements >= tau) kept per C
 constexpr int kFill = 0x7fffff00;     // candidate indices >= kFill are fillers ("no candidate"), distinct so that ranks are unique
 static_assert(kSelMax <= kRsGroups, "the threshold needs at least nsel groups");
 
-// Taylor coefficients 1/12! .. 1/0! in constant memory: DFMA takes them as constant-bank operands (64-bit literals would
-// be rebuilt with two UMOVs per use).
-__constant__ double kExpPoly[13] = {1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0,
-                                    1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
-__constant__ double kExpRed[3] = {1.4426950408889634074, 6.93147180369123816490e-01, 1.90821492927058770002e-10};
+// exp(d) for d <= 0 in fp64, table driven (Tang 1989): d = (32 k + j) ln2/32 + r with |r| <= ln2/64, so
+// exp(d) = 2^k * 2^(j/32) * (1 + expm1(r)) with a 6-term polynomial for expm1 (truncation 3e-18) and a 32-entry table of
+// 2^(j/32) kept in shared memory (indices diverge inside a warp; the constant bank would serialise them).  ~24
+// instructions per value instead of libdevice's ~50, within 1.5 ulp - far inside what the fp32 rounding of logZ can see.
+__constant__ double kExp2Table[32] = {1.00000000000000000e+00, 1.02189714865411663e+00, 1.04427378242741375e+00, 1.06714040067682370e+00, 1.09050773266525769e+00, 1.11438674259589243e+00, 1.13878863475669156e+00, 1.16372485877757748e+00, 1.18920711500272103e+00, 1.21524735998046896e+00, 1.24185781207348400e+00, 1.26905095719173322e+00, 1.29683955465100964e+00, 1.32523664315974132e+00, 1.35425554693689265e+00, 1.38390988196383202e+00, 1.41421356237309515e+00, 1.44518080697704665e+00, 1.47682614593949935e+00, 1.50916442759342284e+00, 1.54221082540794074e+00, 1.57598084510788650e+00, 1.61049033194925428e+00, 1.64575547815396495e+00, 1.68179283050742900e+00, 1.71861929812247793e+00, 1.75625216037329945e+00, 1.79470907500310717e+00, 1.83400808640934243e+00, 1.87416763411029996e+00, 1.91520656139714740e+00, 1.95714412417540018e+00};
+__constant__ double kExpRed[3] = {46.1662413084468283841, 2.16608493865351192653e-02, 5.96317165397058656257e-12};   // 32/ln2, ln2/32 hi, lo
 
-// exp(d) for d <= 0 in fp64: k = rint(d log2 e), r = d - k ln2 (two-term Cody-Waite), degree-12 Taylor polynomial
-// (|r| <= 0.3466: truncation 1.7e-16 relative), scaled by 2^k through the exponent field.  Within 2 ulp - far inside what
-// the fp32 rounding of logZ can see - at ~17 DFMA instead of libdevice's branchy exp.
-__device__ __forceinline__ double exp_nonpos(double d) {
-  d = fmax(d, -700.0);                               // exp(-700) ~ 1e-304: contributes nothing; keeps 2^k a normal number
+__device__ __forceinline__ double exp_nonpos(double d, const double* __restrict__ tbl) {
+  d = fmax(d, -700.0);                               // exp(-700) ~ 1e-304: contributes nothing; keeps the result a normal number
   const double kd = rint(d * kExpRed[0]);
   double r = fma(-kd, kExpRed[1], d);
   r = fma(-kd, kExpRed[2], r);
-  double p = kExpPoly[0];
-#pragma unroll
-  for (int i = 1; i < 13; ++i) p = fma(p, r, kExpPoly[i]);
-  return p * __hiloint2double(((int)kd + 1023) << 20, 0);
+  double q = 1.0 / 720.0;
+  q = fma(q, r, 1.0 / 120.0);
+  q = fma(q, r, 1.0 / 24.0);
+  q = fma(q, r, 1.0 / 6.0);
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  const double p = q * r;                            // expm1(r)
+  const int k = (int)kd;
+  const double t = tbl[k & 31];
+  const double res = fma(t, p, t);                   // 2^(j/32) * exp(r), in [0.98, 2)
+  return __hiloint2double(__double2hiint(res) + (k >> 5) * (1 << 20), __double2loint(res));   // * 2^floor(k/32)
 }
 
-__global__ void __cluster_dims__(kRsChunks, 1, 1) __launch_bounds__(kRsThreads, 3)
+__global__ void __cluster_dims__(kRsChunks, 1, 1) __launch_bounds__(kRsThreads, 4)
 row_select_cluster_kernel(int V, const float* __restrict__ logits, int64_t ldl, int mode, const float* __restrict__ row_bias,
                           float temperature, const int32_t* __restrict__ ban_tokens, const int32_t* __restrict__ ban_count,
                           int ban_stride, int nsel, float* __restrict__ sel_val, int32_t* __restrict__ sel_idx, float* __restrict__ logz) {
@@ -194,6 +199,7 @@ row_select_cluster_kernel(int V, const float* __restrict__ logits, int64_t ldl, 
   __shared__ int s_cnt;
   __shared__ float s_cv[kSelMax];                    // this CTA's nsel best, best first
   __shared__ int s_ci[kSelMax];
+  __shared__ double s_exp2[32];                      // 2^(j/32)
   __shared__ float s_allv[kRsChunks * kSelMax];      // rank 0: the lists of all four CTAs (written by the peers)
   __shared__ int s_alli[kRsChunks * kSelMax];
   pdl_wait();
@@ -209,6 +215,7 @@ row_select_cluster_kernel(int V, const float* __restrict__ logits, int64_t ldl, 
     v[s] = (idx < V) ? x[idx] : -INFINITY;
   }
   if (tid == 0) s_cnt = 0;
+  if (tid < 32) s_exp2[tid] = kExp2Table[tid];
   float lz = 0.f;
   const bool need_lz = (mode == 0 || logz != nullptr);
   if (need_lz) {
@@ -225,7 +232,7 @@ row_select_cluster_kernel(int V, const float* __restrict__ logits, int64_t ldl, 
       const double md = (double)m;
       // no bounds test per slot: slots past the vocabulary hold -inf and add exp(-700) ~ 1e-304, i.e. nothing
 #pragma unroll
-      for (int s = 0; s < kRsSlots; ++s) acc += exp_nonpos((double)v[s] - md);
+      for (int s = 0; s < kRsSlots; ++s) acc += exp_nonpos((double)v[s] - md, s_exp2);
     }
     acc = warp_sum(acc);
     if (lane == 0) s_d[warp] = acc;
@@ -247,7 +254,7 @@ row_select_cluster_kernel(int V, const float* __restrict__ logits, int64_t ldl, 
       double gm = pm;
 #pragma unroll
       for (int o = 2; o > 0; o >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, o));
-      double term = (lane < kRsChunks && pm > -INFINITY) ? ps * exp_nonpos(pm - gm) : 0.0;
+      double term = (lane < kRsChunks && pm > -INFINITY) ? ps * exp_nonpos(pm - gm, s_exp2) : 0.0;
       // fixed order 0+1, 2+3, then the pair sums: identical in all four CTAs
       term += __shfl_xor_sync(0xffffffffu, term, 1);
       term += __shfl_xor_sync(0xffffffffu, term, 2);
