@@ -5,13 +5,17 @@
 // 718,725,753-757), the image embedding (:1415), VLFusion (models/visual_dialog_model.py:127-128), the decoder
 // layers and the LM head (models/visual_dialog_decoder.py:300-311,329-339).
 //
-// Design (one CTA per SM, persistent over output tiles, warp specialised):
-//   warp 0      : TMA producer  - cp.async.bulk.tensor.2d loads of the A (128 x 64) and W (BN x 64) k-blocks into a
-//                 STAGES-deep shared-memory ring (128-byte swizzle), completion on mbarriers
-//   warp 1      : MMA issuer    - one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per k-block
+// Design (persistent over output tiles, warp specialised; one CTA per SM, two in the shared-SM decode configuration):
+//   warp 0      : TMA producer  - cp.async.bulk.tensor loads of the A (128 rows) and W (BN rows) k-blocks into a shared-
+//                 memory ring (128-byte swizzle), completion on mbarriers.  Wide tiles move one 64-element k-chunk per
+//                 2-D box; the narrow decode tiles move several chunks per 3-D box (one thread issues a TMA operation
+//                 every ~0.13 us).  The weights of the first ring are requested before griddepcontrol.wait (PDL).
+//   warp 1      : MMA issuer    - one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per k-chunk
 //                 into one of two TMEM accumulator stages; tcgen05.commit releases ring slots / signals the epilogue
-//   warps 2..9  : epilogue      - tcgen05.ld (32 lanes x 32 columns per warp), + bias, GELU, convert, transpose through a
-//                 warp-private shared-memory tile, row-contiguous (coalesced) global stores.
+//   warps 2..   : epilogue      - 16 warps (4 per TMEM lane quadrant; 4 in the shared-SM configuration): tcgen05.ld
+//                 (32 lanes x 32 columns), + bias, GELU, convert, then either a swizzled shared-memory tile + TMA store
+//                 (throughput problems), direct 16-byte row stores (skinny decode problems) or the generic
+//                 transpose-through-shared-memory path (outputs a tensor map cannot describe).
 //                 Two accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
 // Both operands are K-major ("TN"), which is the layout of activations [rows, features] and nn.Linear weights
 // [out, in], so no transposes are ever materialised.  TMA zero-fills out-of-range rows / k, so M, N, K need not be
