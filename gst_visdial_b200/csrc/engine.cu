@@ -620,7 +620,7 @@ void do_generate(gstvd_ctx* c, int B, const gstvd_gen_params& gp, const int64_t*
       cudaGraph_t graph;
       CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
       try {
-        decode_step(c, g, gp, hist_ids, hist_seg, Lh, s);
+        for (int t = 0; t < T; ++t) decode_step(c, g, gp, hist_ids, hist_seg, Lh, s);   // all T steps in ONE graph: no host round trip between steps
       } catch (...) {
         cudaGraph_t dead; cudaStreamEndCapture(s, &dead);
         throw;
@@ -630,11 +630,11 @@ void do_generate(gstvd_ctx* c, int B, const gstvd_gen_params& gp, const int64_t*
       CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
       CUDA_CHECK(cudaGraphDestroy(graph));
       it = c->graphs.emplace(key, exec).first;
-      c->graph_kernels[key] = c->launches - before;   // kernels per replay = what the captured step enqueued
+      c->graph_kernels[key] = c->launches - before;   // kernels per replay = what the captured steps enqueued
       c->launches = before;                           // capture itself launches nothing
     }
-    const int64_t per_step = c->graph_kernels[key];
-    for (int t = 0; t < T; ++t) { CUDA_CHECK(cudaGraphLaunch(it->second, s)); c->launches += per_step; }
+    CUDA_CHECK(cudaGraphLaunch(it->second, s));
+    c->launches += c->graph_kernels[key];
   }
   if (gp.mode == GSTVD_SELECT_BEAM) c->launches += launch_beam_finalize(beam_buffers(c), B, K, T, 102, out_ids, out_scores, s);
   else c->launches += launch_sample_finalize(B, T, 102, (const int32_t*)c->seq.p, out_ids, s);
