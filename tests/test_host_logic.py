@@ -94,3 +94,34 @@ def test_gather_world2_gloo(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_scores_to_ranks_matches_reference_loops():
+    """utils/visdial_metrics.py:21-39 restated literally (two Python loops) vs the vectorised scatter; metrics sanity."""
+    import torch
+    from gst_visdial_b200.ranking import scores_to_ranks, sparse_metrics
+    g = torch.Generator().manual_seed(3)
+    scores = torch.randn(3, 4, 11, generator=g)
+    flat = scores.view(-1, 11)
+    ranked_idx = flat.sort(1, descending=True)[1]
+    ref = ranked_idx.clone().fill_(0)
+    for i in range(ranked_idx.size(0)):
+        for j in range(11):
+            ref[i][ranked_idx[i][j]] = j
+    ref = (ref + 1).view(3, 4, 11)
+    assert torch.equal(scores_to_ranks(scores), ref)
+    m = sparse_metrics(torch.tensor([1, 2, 6, 11]))
+    assert m["r@1"] == 0.25 and m["r@5"] == 0.5 and m["r@10"] == 0.75 and abs(m["mean"] - 5.0) < 1e-6
+
+
+def test_synthetic_eval_items_are_reproducible_and_well_formed():
+    import torch
+    from gst_visdial_b200.eval_synthetic import synthetic_eval_item
+    b1, o1, g1 = synthetic_eval_item(4, 3, 2, 9, 30522, 64)
+    b2, o2, g2 = synthetic_eval_item(4, 3, 2, 9, 30522, 64)
+    assert torch.equal(o1, o2) and torch.equal(g1, g2) and torch.equal(b1["enc_input_ids"], b2["enc_input_ids"])
+    assert o1.shape == (3, 9, 25) and (o1[:, :, 0] == 101).all() and ((o1 == 102).sum(-1) == 1).all()
+    ids = b1["enc_input_ids"]
+    n = (ids != 0).sum(-1)
+    assert ((ids != 0).long().cumsum(-1)[torch.arange(3), n - 1] == n).all()          # no holes: tokens are a prefix
+    assert (b1["enc_att_mask"] == (ids != 0).float()).all() and (n > 40).all()         # caption + two rounds + a question
