@@ -235,8 +235,7 @@ def main():
     for si in range(S_):
         params = {"model_enc_config": W.DEFAULT_ENC_CONFIG, "model_dec_config": W.DEFAULT_DEC_CONFIG, "gpu_ids": [local], "model": "enc_dec_a",
                   "mode": "cc12m_gen", "compute_dtype": a.dtype, "engine_max_batch": a.batch, "engine_max_beams": max(a.beams, 1),
-                  # several contexts share the GPU from separate streams: decode GEMMs in the 2-CTA-per-SM configuration
-                  "engine_flags": _lib.GSTVD_FLAG_SHARED_SM_GEMM if a.streams > 1 else 0}
+                  "engine_flags": 0}
         enc, dec = VisualDialogEncoder(params), VisualDialogDecoder(params)
         dec.decoder.bert.embeddings = enc.bert_pretrained.bert.embeddings
         model = EncoderDecoderModel(params, enc, dec)

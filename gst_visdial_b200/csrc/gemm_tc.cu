@@ -39,9 +39,9 @@ constexpr int BM = 128;          // rows per tile  (UMMA M)
 constexpr int BK = 64;           // k per stage: 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 // Epilogue warps: 16 (4 per TMEM lane quadrant) for the throughput configurations - the epilogue is ALU/latency bound and
-// needs the warps; 4 (one per quadrant) for the "skinny" decode configuration, whose 6-warp CTA with ~100 KB of shared
-// memory lets TWO CTAs share an SM: decode GEMMs (M = 320) are latency bound, so a co-resident CTA - the next GEMM of the
-// same stream under PDL, or another stream's - fills the SM time this one spends waiting.
+// needs the warps; 4 (one per quadrant) for the "skinny" decode configuration (64-row tiles, see TileCfg), whose 6-warp CTA
+// with ~100 KB of shared memory lets TWO CTAs share an SM: decode GEMMs (M = 320) are latency bound, so a co-resident CTA -
+// the next GEMM of the same stream under PDL, or another stream's - fills the SM time this one spends waiting.
 constexpr int kEpiWarpsWide = 16;
 constexpr int kEpiWarpsSkinny = 4;
 constexpr unsigned long long kWaitTimeoutNs = 4000000000ull;   // 4 s: far beyond any legitimate wait
@@ -180,23 +180,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 template <int BN, int EW> struct TileCfg {
   static constexpr bool kSkinny = EW == kEpiWarpsSkinny;
   static constexpr int kThreads = (2 + EW) * 32;
-  // k-chunks (64 elements each) per pipeline stage.  The narrow tiles serve the M <= 384 decode GEMMs, whose main loop is
+  // Rows per tile = UMMA M.  The skinny (decode, M = 320) configuration uses M = 64: five exact row tiles instead of three
+  // 128-row tiles with 17 % padding, 40 % fewer bytes through the L2->SM port per CTA ((64+BN) instead of (128+BN) rows per
+  // k-step) on more SMs, and a CTA small enough for two per SM.  The M = 64 accumulator occupies lanes 0-15 of every
+  // 32-lane TMEM quadrant: row r lives in lane (r / 16) * 32 + r % 16 (tools/probes/umma_m64_layout.cu).
+  static constexpr int kBM = kSkinny ? 64 : BM;
+  // k-chunks (64 elements each) per pipeline stage.  The narrow tiles serve the M <= 512 decode GEMMs, whose main loop is
   // bound by the RATE of TMA operations issued by one thread (~0.13 us each), not by bytes: one 3-D box
-  // {64, rows, 4 chunks} moves four k-blocks per operation.
-  static constexpr int kCK = kSkinny ? 2 : (BN <= 64 ? 4 : 1);
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 2);
-  static constexpr int kAChunk = BM * BK * 2;                  // one 128-row x 64-element SW128 tile
+  // {64, rows, chunks} moves several k-blocks per operation.
+  static constexpr int kCK = kSkinny ? (BN <= 32 ? 4 : 2) : (BN <= 64 ? 4 : 1);
+  static constexpr int kStages = kSkinny ? (BN <= 32 ? 2 : 3) : (BN == 256 ? 4 : (BN == 128 ? 6 : 2));
+  static constexpr int kAChunk = kBM * BK * 2;                 // one kBM-row x 64-element SW128 tile
   static constexpr int kBChunk = BN * BK * 2;
   static constexpr int kABytes = kAChunk * kCK;
   static constexpr int kBBytes = kBChunk * kCK;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // power of two for BN in {16,32,64,128,256}
   static constexpr int kBarBytes = 256;
   static constexpr int kStageWords = 32 * 33;                   // per epilogue warp: 32 rows x 32 words, padded rows
-  // wide: 33 KB = 4 x 8 KB (bf16) / 2 x 16 KB (fp32) TMA-store tiles, or 8 generic tiles; skinny: one group, 4 generic tiles
-  static constexpr int kStagingBytes = (kSkinny ? 4 : 8) * kStageWords * 4;
-  // The wide configurations keep 1 KB of alignment slack; the skinny ones must fit twice into an SM (2 x (bytes + 1 KB
-  // reserved) <= 228 KB) and rely on the 1024-byte alignment of the dynamic shared-memory window (checked at run time).
-  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kBarBytes + kStagingBytes + (kSkinny ? 0 : 1024);
+  // wide: 33 KB = 4 x 8 KB (bf16) / 2 x 16 KB (fp32) TMA-store tiles, or 8 generic tiles; skinny: none (direct row stores only)
+  static constexpr int kStagingBytes = kSkinny ? 0 : 8 * kStageWords * 4;
+  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kBarBytes + kStagingBytes + 1024;   // +1024: alignment slack
   static_assert(!kSkinny || 2 * (kSmemBytes + 1024) <= 233472, "skinny configuration must fit two CTAs per SM");
 };
 
@@ -464,7 +467,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // 128B-swizzle atoms need 1024-byte alignment
-  if (Cfg::kSkinny && base != raw) __trap();                    // no slack in the skinny layout
   const uint32_t a_base = base;
   const uint32_t b_base = base + kStages * Cfg::kABytes;
   const uint32_t stage_base = b_base + kStages * Cfg::kBBytes;   // epilogue staging (1024-byte aligned: TMA-store source)
@@ -482,7 +484,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   unsigned long long* stamps = p.dbg_times ? p.dbg_times + (size_t)blockIdx.x * 8 : nullptr;
   if (stamps && threadIdx.x == 0) stamps[0] = global_ns();
   const int tiles_n = (p.N + BN - 1) / BN;
-  const int tiles_m = p.hm_tpi > 0 ? p.hm_B * p.hm_tpi : (p.M + BM - 1) / BM;
+  constexpr int kBM = Cfg::kBM;
+  const int tiles_m = p.hm_tpi > 0 ? p.hm_B * p.hm_tpi : (p.M + kBM - 1) / kBM;
   const int num_tiles = tiles_m * tiles_n;
   constexpr int kCK = Cfg::kCK;
   const int num_kb = (p.K + BK * kCK - 1) / (BK * kCK);      // pipeline stages per tile
@@ -514,7 +517,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       };
       auto load_a = [&](int st, int kb, int m_blk) {
         if constexpr (kCK > 1) {
-          tma_load_3d(a_base + st * Cfg::kABytes, &tm_a, 0, m_blk * BM, kb * kCK, full_bar(st));
+          tma_load_3d(a_base + st * Cfg::kABytes, &tm_a, 0, m_blk * kBM, kb * kCK, full_bar(st));
         } else if (p.hm_tpi > 0) {
           const int img = m_blk / p.hm_tpi;
           tma_load_3d(a_base + st * Cfg::kABytes, &tm_a, kb * BK, (m_blk - img * p.hm_tpi) * BM, img, full_bar(st));
@@ -552,7 +555,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+      constexpr uint32_t idesc = make_idesc(kBM, BN);
       int stage = 0; uint32_t phase = 0; int iter = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
         const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
@@ -624,8 +627,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           const int col0 = n_blk * BN + j * 32;
           if (col0 >= p.N) break;
           const float* bp = (have_bpre && j == grp) ? bpre : nullptr;
-          if (p.out_f32) epilogue_direct_block<float>(p, tq + j * 32, row0 + lane, col0, bp);
-          else epilogue_direct_block<bf16>(p, tq + j * 32, row0 + lane, col0, bp);
+          // M = 128: TMEM lane == tile row.  M = 64: lanes 0-15 of each quadrant hold rows quad * 16 + lane, the rest nothing.
+          const int row = kBM == 128 ? row0 + lane : (lane < 16 ? m_blk * kBM + quad * 16 + lane : p.M);
+          if (p.out_f32) epilogue_direct_block<float>(p, tq + j * 32, row, col0, bp);
+          else epilogue_direct_block<bf16>(p, tq + j * 32, row, col0, bp);
         }
       } else if (p.tma_store) {
         const int r = quad * 32 + lane;                     // accumulator row == TMEM lane == staging row
@@ -787,7 +792,7 @@ void launch_cfg(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
     attr_set = true;
   }
   GemmArgs a = a_in;
-  const CUtensorMap* ma_ptr = Cfg::kCK > 1 ? &get_map_k3(a.A, a.M, a.K, a.lda, BM, Cfg::kCK) : &get_map(a.A, a.M, a.K, a.lda, BM);
+  const CUtensorMap* ma_ptr = Cfg::kCK > 1 ? &get_map_k3(a.A, a.M, a.K, a.lda, Cfg::kBM, Cfg::kCK) : &get_map(a.A, a.M, a.K, a.lda, Cfg::kBM);
   const CUtensorMap& mb = Cfg::kCK > 1 ? get_map_k3(a.W, a.N, a.K, a.ldw, BN, Cfg::kCK) : get_map(a.W, a.N, a.K, a.ldw, BN);
   // TMA-store epilogue when the output is expressible as a tensor map; otherwise the generic register/shared path
   const int esz = a.out_f32 ? 4 : 2;
@@ -815,8 +820,9 @@ void launch_cfg(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
       }
     }
   }
-  const int tiles_m = a.hm_tpi > 0 ? a.hm_B * a.hm_tpi : (a.M + BM - 1) / BM;
+  const int tiles_m = a.hm_tpi > 0 ? a.hm_B * a.hm_tpi : (a.M + Cfg::kBM - 1) / Cfg::kBM;
   const int tiles = tiles_m * ((a.N + BN - 1) / BN);
+  if (Cfg::kSkinny && a.tma_store != 2) throw std::runtime_error("gemm_tc: the skinny configuration only has the direct-store epilogue");
   const int slots = Cfg::kSkinny ? 2 * num_sms : num_sms;      // resident CTAs: the kernel is persistent over the remaining tiles
   const int grid = tiles < slots ? tiles : slots;
   launch_k(gemm_tc_kernel<BN, EW>, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmemBytes, stream, *ma_ptr, mb, *mc, a);
@@ -880,12 +886,24 @@ int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream, bool 
   }
   if (bn_env) bn = bn_env;
   if (bn <= 64 && a.K % BK != 0) bn = 128;               // the chunked (3-D box) operand view needs whole 64-element chunks
+  // Skinny (decode) problems whose output qualifies for direct row stores run the M = 64 configuration (two CTAs per SM):
+  // 32-column tiles when they all fit the 2 x SMs resident slots, else 64-column tiles.
   static const int skinny_env = [] { const char* e = getenv("GSTVD_GEMM_SKINNY"); return e ? atoi(e) : -1; }();   // A/B aid: force 0 / 1
-  const bool skinny = skinny_env >= 0 ? skinny_env != 0 : shared_sm;
-  if (tiles_m <= 4 && bn <= 64 && skinny && a.K % BK == 0 && a.hm_D == 0) {
-    if (bn == 64) launch_cfg<64, kEpiWarpsSkinny>(a, num_sms, stream);
-    else launch_cfg<32, kEpiWarpsSkinny>(a, num_sms, stream);
-    return 1;
+  (void)shared_sm;                                         // kept in the signature: the M = 64 configuration is shared-SM by construction
+  const bool skinny = skinny_env >= 0 ? skinny_env != 0 : true;
+  {
+    const int esz = a.out_f32 ? 4 : 2;
+    const bool direct_ok = a.hm_D == 0 && (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (a.ldc * esz) % 16 == 0 && a.M <= 4 * BM &&
+                           (int64_t)a.M * a.N * esz <= (4 << 20) && getenv("GSTVD_GEMM_NO_DIRECT") == nullptr &&
+                           getenv("GSTVD_GEMM_NO_TMA_STORE") == nullptr;
+    if (skinny && direct_ok && a.K % BK == 0 && !bn_env) {
+      const int tm64 = (a.M + 63) / 64;
+      if (tm64 * ((a.N + 31) / 32) <= 2 * num_sms) { launch_cfg<32, kEpiWarpsSkinny>(a, num_sms, stream); return 1; }
+      // wider outputs (N = 2304 / 3072 at M = 320) measured faster in the 128-row configuration with 16 epilogue warps
+      // (5.5 / 5.7 us vs 5.9 / 6.2 us): 64-column tiles make each of the four epilogue warps handle two column blocks
+      static const bool wide64 = getenv("GSTVD_GEMM_SKINNY64") != nullptr;
+      if (wide64 && tm64 * ((a.N + 63) / 64) <= 2 * num_sms) { launch_cfg<64, kEpiWarpsSkinny>(a, num_sms, stream); return 1; }
+    }
   }
   switch (bn) {
     case 256: launch_cfg<256>(a, num_sms, stream); break;

@@ -78,8 +78,8 @@ typedef struct {
 #define GSTVD_FLAG_DEBUG_SIMT_GEMM 2 /* debugging aid: route bf16 GEMMs through the SIMT kernel */
 #define GSTVD_FLAG_NO_PDL 8          /* decode-step kernels without programmatic dependent launch */
 #define GSTVD_FLAG_GENERIC_ATTENTION 4 /* debugging aid: route bf16 attention through the generic SIMT kernel */
-#define GSTVD_FLAG_SHARED_SM_GEMM 16  /* decode-step GEMMs in the 2-CTA-per-SM configuration: ~8 % slower alone, but two contexts
-                                        * driving one GPU from separate streams overlap their (latency-bound) decode steps */
+#define GSTVD_FLAG_SHARED_SM_GEMM 16  /* accepted for compatibility, no effect: the decode-step GEMMs always run the 64-row configuration
+                                        * of which two CTAs share an SM, so contexts on separate streams overlap their decode steps */
 
 typedef struct {
   int32_t mode;               /* gstvd_select_mode */
