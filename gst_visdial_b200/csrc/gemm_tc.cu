@@ -898,7 +898,8 @@ int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream, bool 
                            getenv("GSTVD_GEMM_NO_TMA_STORE") == nullptr;
     if (skinny && direct_ok && a.K % BK == 0 && !bn_env) {
       const int tm64 = (a.M + 63) / 64;
-      if (tm64 * ((a.N + 31) / 32) <= 2 * num_sms) { launch_cfg<32, kEpiWarpsSkinny>(a, num_sms, stream); return 1; }
+      static const int multi = [] { const char* e = getenv("GSTVD_GEMM_SKINNY_WAVES"); return e ? atoi(e) : 1; }();   // A/B aid
+      if (tm64 * ((a.N + 31) / 32) <= 2 * num_sms * multi) { launch_cfg<32, kEpiWarpsSkinny>(a, num_sms, stream); return 1; }
       // wider outputs (N = 2304 / 3072 at M = 320) measured faster in the 128-row configuration with 16 epilogue warps
       // (5.5 / 5.7 us vs 5.9 / 6.2 us): 64-column tiles make each of the four epilogue warps handle two column blocks
       static const bool wide64 = getenv("GSTVD_GEMM_SKINNY64") != nullptr;
