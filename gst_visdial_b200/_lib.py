@@ -74,6 +74,7 @@ SYMBOLS = [
     ("gstvd_splice", c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, c_int, _P, _P]),
     ("gstvd_op_linear", c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P]),
     ("gstvd_op_add_layernorm", c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
+    ("gstvd_op_linear_add_layernorm", c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P]),
     ("gstvd_op_attention", c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_float, c_int, _P, _P]),
     ("gstvd_op_beam_begin", c_int, [_P, c_int, c_int, c_int, _P]),
     ("gstvd_op_beam_step", c_int, [_P, _P, c_int64, _P, _P, _P, _P]),

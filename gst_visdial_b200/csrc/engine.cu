@@ -354,6 +354,19 @@ struct Exec {
   void add_ln(const void* x, const void* res, const LNp& l, void* y, int rows) {
     c->launches += launch_add_layernorm(dt(), rows, l.n, x, l.n, res, l.n, l.g, l.b, y, l.n, s);
   }
+  // y = LN(A L^T + bias + res): the fused cluster kernel when enabled (env GSTVD_FUSE_LN) and applicable, else GEMM into tmp + add_ln
+  void gemm_add_ln(const void* A, int64_t lda, const Linear& L, const void* res, const LNp& l, void* tmp, void* y, int M) {
+    const int mode = gemm_ln_mode();
+    if (mode != 0 && c->dtype == kBF16 && !(c->cfg.flags & GSTVD_FLAG_DEBUG_SIMT_GEMM) && l.n == L.out &&
+        gemm_ln_tc_supported(M, L.out, L.in, A, lda, L.w16, L.in, res, l.n, y, l.n)) {
+      GemmArgs a;
+      a.A = A; a.lda = lda; a.W = L.w16; a.ldw = L.in; a.bias = L.b; a.M = M; a.N = L.out; a.K = L.in;
+      c->launches += launch_gemm_ln_tc(a, res, l.n, l.g, l.b, 1e-12f, y, l.n, mode, s);
+      return;
+    }
+    gemm(A, lda, L, tmp, L.out, M);
+    add_ln(tmp, res, l, y, M);
+  }
   // q/k/v: rows of `ld` elements holding all heads; one batch = L rows
   void attention(const void* q, int64_t ldq, int Lq, const void* k, const void* v, int64_t ldkv, int Lk, void* o, int64_t ldo,
                  int B, int heads, int D, const float* kmask, float neg, int causal) {
@@ -538,19 +551,16 @@ void decode_step(gstvd_ctx* c, const DecodeGeom& g, const gstvd_gen_params& gp, 
     const DecLayer& L = c->d_layers[l];
     X.gemm(c->dh.p, H, L.qkv, c->dqkv.p, 3 * H, M);
     c->launches += launch_dec_self_attn(c->dtype, g, l, c->dqkv.p, c->self_cache.p, d_step, c->dctx.p, s);
-    X.gemm(c->dctx.p, H, L.o, c->dtmp.p, H, M);
-    X.add_ln(c->dtmp.p, c->dh.p, L.ln_att, c->da.p, M);
+    X.gemm_add_ln(c->dctx.p, H, L.o, c->dh.p, L.ln_att, c->dtmp.p, c->da.p, M);
     X.gemm(c->da.p, H, L.cq, c->dqc.p, H, M);
     if (dec_cross_tma_supported(c->dtype, g))
       c->launches += launch_dec_cross_tma(g, l, c->dqc.p, c->cross_cache.p, (const float*)c->fused_mask.p, (const int*)c->cross_len.p, c->dctx.p,
                                           c->num_sms, s);
     else
       c->launches += launch_dec_cross_attn(c->dtype, g, l, c->dqc.p, c->cross_cache.p, (const float*)c->fused_mask.p, c->dctx.p, s);
-    X.gemm(c->dctx.p, H, L.co, c->dtmp.p, H, M);
-    X.add_ln(c->dtmp.p, c->da.p, L.ln_cross, c->db.p, M);
+    X.gemm_add_ln(c->dctx.p, H, L.co, c->da.p, L.ln_cross, c->dtmp.p, c->db.p, M);
     X.gemm(c->db.p, H, L.f1, c->dffn.p, c->dec_F, M, 1);
-    X.gemm(c->dffn.p, c->dec_F, L.f2, c->dtmp.p, H, M);
-    X.add_ln(c->dtmp.p, c->db.p, L.ln_out, c->dh.p, M);
+    X.gemm_add_ln(c->dffn.p, c->dec_F, L.f2, c->db.p, L.ln_out, c->dtmp.p, c->dh.p, M);
   }
   X.gemm(c->dh.p, H, c->lm_head, c->logits.p, c->Vpad, M, 0, true);
   float* sv = (float*)c->sel_val.p; int32_t* si = (int32_t*)c->sel_idx.p;
@@ -1000,6 +1010,29 @@ int gstvd_op_add_layernorm(gstvd_ctx* c, int dtype, int rows, int width, const f
       c->launches += launch_cast_to_f32(kBF16, y16, y, n, s);
       CUDA_CHECK(cudaStreamSynchronize(s));
     }
+  });
+}
+
+int gstvd_op_linear_add_layernorm(gstvd_ctx* c, int M, int K, const float* a, const float* w, const float* bias, const float* residual,
+                                  const float* gamma, const float* beta, int cluster, float* y, void* stream) {
+  if (!c) return GSTVD_ERR_INVALID;
+  return guarded(c, [&] {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int N = 768;
+    if (M < 1 || K < 1 || K % 256 != 0) throw InvalidArg("op_linear_add_layernorm: K must be a positive multiple of 256");
+    if (!a || !w || !gamma || !beta || !y) throw InvalidArg("op_linear_add_layernorm: NULL buffer");
+    if (cluster != 8 && cluster != 16) throw InvalidArg("op_linear_add_layernorm: cluster must be 8 or 16");
+    Scratch sc;
+    void* a16 = sc.get((size_t)M * K * 2); void* w16 = sc.get((size_t)N * K * 2);
+    void* r16 = residual ? sc.get((size_t)M * N * 2) : nullptr; void* y16 = sc.get((size_t)M * N * 2);
+    c->launches += launch_cast_f32_to(kBF16, a, a16, (int64_t)M * K, s);
+    c->launches += launch_cast_f32_to(kBF16, w, w16, (int64_t)N * K, s);
+    if (residual) c->launches += launch_cast_f32_to(kBF16, residual, r16, (int64_t)M * N, s);
+    GemmArgs g;
+    g.A = a16; g.lda = K; g.W = w16; g.ldw = K; g.bias = bias; g.M = M; g.N = N; g.K = K;
+    c->launches += launch_gemm_ln_tc(g, r16, N, gamma, beta, 1e-12f, y16, N, cluster, s);
+    c->launches += launch_cast_to_f32(kBF16, y16, y, (int64_t)M * N, s);
+    CUDA_CHECK(cudaStreamSynchronize(s));
   });
 }
 

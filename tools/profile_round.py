@@ -57,3 +57,13 @@ e1.record()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print(f"one round: {e0.elapsed_time(e1):.2f} ms (not a bench value when run under a profiler); ids[0,:6]={ids[0,:6].tolist()}")
+# the decode part alone (18 steps replayed from the graph), mean of 5, plus a checksum of the ids for A/B runs of experimental flags
+g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+g0.record()
+for _ in range(5):
+    ids = eng.generate(a.batch, num_beams=a.beams)
+g1.record()
+torch.cuda.synchronize()
+w = torch.arange(1, ids.numel() + 1, device=ids.device, dtype=torch.int64).view_as(ids)
+print(f"generate only: {g0.elapsed_time(g1) / 5:.3f} ms per call; ids checksum {int((ids * w).sum())}; "
+      f"FUSE_LN={os.environ.get('GSTVD_FUSE_LN', '0')}")
