@@ -144,6 +144,104 @@ dec_self_attn_kernel(DecodeGeom g, int layer, const T* __restrict__ qkv, T* __re
     if (u < nd) o[lane + 32 * u] = from_f32<T>(acc[u]);
 }
 
+// bf16, D = 64 variant with a third of the instructions (the kernel above is issue-bound: ~1100 warp instructions per (row, head),
+// 56 % issue-slot utilisation in ncu).  One warp per (row, head); a cached key / value row is 128 bytes = eight 16-byte chunks, so
+// eight lanes own one position and the warp covers four positions per load instruction: lane = 8 * (position % 4) + chunk.
+//   * every load of the kernel - q / k / v of the new position, *d_step, the K and V rows of ALL g.T cache positions - is issued
+//     in one batch right after the PDL wait (rows past *d_step are allocated; their scores are masked afterwards), so the kernel
+//     pays ONE memory round trip instead of three dependent ones;
+//   * scores: 8 FMAs per lane + a 3-step butterfly inside the 8-lane group; softmax statistics: 2-step butterflies across groups;
+//   * P * V: each lane accumulates its 8 dims over its positions, one 2-step butterfly per dim merges the four groups and lanes 0-7
+//     store the 128-byte output row.
+// The new position's k / v are taken from qkv (rounded to bf16, i.e. exactly what later steps will read back from the cache).
+template <int NIT>
+__global__ void __launch_bounds__(128)
+dec_self_attn_v2_kernel(DecodeGeom g, int layer, const bf16* __restrict__ qkv, bf16* __restrict__ cache, const int* __restrict__ d_step,
+                        const uint8_t* __restrict__ anc, bf16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x;
+  const int h = blockIdx.y * 4 + warp;
+  if (h >= g.heads) return;
+  const int b = row / g.K, kb = row - b * g.K;
+  const int H = g.H;
+  const int chunk = lane & 7, grp = lane >> 3;
+  const bf16* qrow = qkv + (int64_t)row * 3 * H + h * 64 + chunk * 8;
+  const uint4 q_raw = *reinterpret_cast<const uint4*>(qrow);
+  const uint4 kn_raw = *reinterpret_cast<const uint4*>(qrow + H);
+  const uint4 vn_raw = *reinterpret_cast<const uint4*>(qrow + 2 * H);
+  const int step = *d_step;
+  // element offset of (kv, position t) for this beam / head / chunk
+  const int64_t pos_stride = (int64_t)g.K * H;
+  const int64_t k_base = ((((int64_t)layer * 2 + 0) * g.B + b) * g.T) * pos_stride + h * 64 + chunk * 8;   // slot 0 of position 0
+  const int64_t v_base = k_base + (int64_t)g.B * g.T * pos_stride;
+  // Beam search without moving the cache (anc != null): position t of this beam's history lives in the slot of the beam that
+  // wrote it, anc[(b*K + kb)*32 + t] (anc_update_kernel permutes the 32-byte rows after every selection); the new position is
+  // always written to the beam's own slot.  Entries at or past *d_step are stale but always < 8; they are clamped and masked.
+  int slot[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int t = it * 4 + grp;
+    slot[it] = anc != nullptr ? min((int)anc[((int64_t)b * g.K + kb) * kMaxSteps + (t & (kMaxSteps - 1))], g.K - 1) : kb;
+  }
+  uint4 k_raw[NIT], v_raw[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int t = it * 4 + grp;
+    const int tc = t < g.T ? t : 0;                  // rows past the cache capacity: any valid address, masked below
+    k_raw[it] = *reinterpret_cast<const uint4*>(cache + k_base + tc * pos_stride + (int64_t)slot[it] * H);
+    v_raw[it] = *reinterpret_cast<const uint4*>(cache + v_base + tc * pos_stride + (int64_t)slot[it] * H);
+  }
+  // append the new position (lanes 0-7: key chunks, lanes 8-15: value chunks)
+  if (grp == 0) *reinterpret_cast<uint4*>(cache + k_base + step * pos_stride + (int64_t)kb * H) = kn_raw;
+  else if (grp == 1) *reinterpret_cast<uint4*>(cache + v_base + step * pos_stride + (int64_t)kb * H) = vn_raw;
+
+  float q[8];
+  Raw16<bf16>::unpack(q_raw, q);
+  float sc[NIT];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int t = it * 4 + grp;
+    if (t == step) { k_raw[it] = kn_raw; v_raw[it] = vn_raw; }
+    float kr[8];
+    Raw16<bf16>::unpack(k_raw[it], kr);
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dot = fmaf(q[j], kr[j], dot);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+    sc[it] = t <= step ? dot * 0.125f : -INFINITY;   // 1 / sqrt(64), exact
+    mx = fmaxf(mx, sc[it]);
+  }
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+  float sum = 0.f;
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) { sc[it] = expf(sc[it] - mx); sum += sc[it]; }   // exp(-inf) = 0 for the masked slots
+  sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const float pr = sc[it] / sum;
+    float vr[8];
+    Raw16<bf16>::unpack(v_raw[it], vr);
+    if (it * 4 + grp <= step) {                      // stale rows may hold anything (NaN bit patterns included): skip, do not scale by 0
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(pr, vr[j], acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+  }
+  if (grp == 0) Vec8<bf16>::store(out + (int64_t)row * H + h * 64 + chunk * 8, acc);
+}
+
 constexpr int kCrossThreads = 320;            // 10 warps: one thread per key in the score phase (Le = 293 in the real model)
 
 template <typename T, int KB, int D>
@@ -479,6 +577,26 @@ void launch_cross_t(const DecodeGeom& g, const void* q, const void* kv_layer, co
   else launch_cross_kb<T, 8>(g, qq, kv, enc_mask, o, stream);
 }
 
+// Beam reorder without moving the cache: new beam k continues old beam parent = beam_idx[b][k]; its history row becomes the
+// parent's row and the position just written (t = *d_step) is found in the parent's slot.  One CTA per image; every entry is
+// read before any is written (parents may repeat).  Replaces reorder_cache_kernel (up to 2 x 100 MB of HBM traffic per step at
+// B = 64, K = 5) when the self-attention kernel reads through the table (dec_self_attn_v2_kernel).
+__global__ void __launch_bounds__(kMaxBeams * kMaxSteps)
+anc_update_kernel(int B, int K, const int32_t* __restrict__ beam_idx, const int* __restrict__ d_step, uint8_t* __restrict__ anc) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.x, k = threadIdx.x / kMaxSteps, t = threadIdx.x % kMaxSteps;
+  const int step = *d_step;
+  int val = 0;
+  const bool live = k < K && t <= step;
+  if (live) {
+    const int parent = beam_idx[b * K + k];
+    val = (t == step) ? parent : anc[((int64_t)b * K + parent) * kMaxSteps + t];
+  }
+  __syncthreads();
+  if (live) anc[((int64_t)b * K + k) * kMaxSteps + t] = (uint8_t)val;
+}
+
 // One CTA per (image, layer*2+kv).  Thread-local dependency only: every thread loads the K source values of its
 // column chunk before it stores any of them, so duplicated parents (beam_idx is not a permutation) are safe in place.
 template <typename T>
@@ -515,11 +633,32 @@ reorder_cache_kernel(DecodeGeom g, T* __restrict__ cache, const int32_t* __restr
 
 }  // namespace
 
+bool dec_self_attn_v2_active(int dtype, const DecodeGeom& g, const void* qkv, const void* self_cache, const void* out) {
+  const char* v2_env = getenv("GSTVD_SELF_V2");            // read per call (captured graphs keep what was set at capture time)
+  const bool v2 = v2_env == nullptr || atoi(v2_env) != 0;  // default on; GSTVD_SELF_V2=0 selects the first kernel
+  return v2 && dtype == kBF16 && g.D == 64 && g.H % 8 == 0 && g.T <= kMaxSteps && g.K <= kMaxBeams &&
+         (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(self_cache) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+}
+
+int launch_anc_update(const DecodeGeom& g, const int32_t* beam_idx, const int* d_step, uint8_t* anc, cudaStream_t stream) {
+  if (g.K > kMaxBeams || g.T > kMaxSteps) throw std::runtime_error("anc_update: at most 8 beams and 32 positions");
+  launch_k(anc_update_kernel, dim3(g.B), dim3(kMaxBeams * kMaxSteps), 0, stream, g.B, g.K, beam_idx, d_step, anc);
+  return 1;
+}
+
 int launch_dec_self_attn(int dtype, const DecodeGeom& g, int layer, const void* qkv, void* self_cache, const int* d_step,
-                         void* out, cudaStream_t stream) {
+                         const uint8_t* anc, void* out, cudaStream_t stream) {
   if (g.D != 64 && g.D != 128) throw std::runtime_error("dec_self_attn: head_dim must be 64 or 128");
   if (g.T > kMaxSteps) throw std::runtime_error("dec_self_attn: at most 32 cached positions");
   dim3 grid(g.B * g.K, (g.heads + 3) / 4);
+  // lean variant: bf16, 64-dim heads, 16-byte aligned rows
+  if (dec_self_attn_v2_active(dtype, g, qkv, self_cache, out)) {
+    if (g.T <= 20) launch_k(dec_self_attn_v2_kernel<5>, grid, dim3(128), 0, stream, g, layer, (const bf16*)qkv, (bf16*)self_cache, d_step, anc, (bf16*)out);
+    else launch_k(dec_self_attn_v2_kernel<8>, grid, dim3(128), 0, stream, g, layer, (const bf16*)qkv, (bf16*)self_cache, d_step, anc, (bf16*)out);
+    return 1;
+  }
+  if (anc != nullptr) throw std::runtime_error("dec_self_attn: the ancestry table is only read by the bf16 / 64-dim kernel");
   if (g.D == 64) {
     if (dtype == kF32) launch_k(dec_self_attn_kernel<float, 2>, grid, dim3(128), 0, stream, g, layer, (const float*)qkv, (float*)self_cache, d_step, (float*)out);
     else launch_k(dec_self_attn_kernel<bf16, 2>, grid, dim3(128), 0, stream, g, layer, (const bf16*)qkv, (bf16*)self_cache, d_step, (bf16*)out);

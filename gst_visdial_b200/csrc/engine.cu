@@ -107,6 +107,7 @@ struct gstvd_ctx {
   DevBuf ban_tokens, ban_count, prefix, seq;          // sample-mode state
   DevBuf beam_scores, beam_tokens, cur_tokens, beam_idx, beam_done, hyp_score, hyp_len, hyp_tokens, hyp_count, hyp_worst;
   DevBuf d_step, d_seed;
+  DevBuf anc;                                         // uint8 [B*K][32]: beam ancestry table (launch_anc_update)
   int enc_B = 0, enc_Le = 0;        // shape of the resident fused states
   int cross_B = 0, cross_Le = 0;    // shape of the resident cross K/V
   // beam op-test state
@@ -317,6 +318,8 @@ void alloc_workspace(gstvd_ctx* c) {
     c->beam_idx.alloc(B * K * 4); c->beam_done.alloc(B); c->hyp_score.alloc(B * (K + 1) * 8);
     c->hyp_len.alloc(B * (K + 1) * 4); c->hyp_tokens.alloc(B * (K + 1) * T * 4); c->hyp_count.alloc(B * 4);
     c->hyp_worst.alloc(B * 8);
+    c->anc.alloc(B * K * 32);
+    CUDA_CHECK(cudaMemset(c->anc.p, 0, B * K * 32));
   }
   c->d_step.alloc(16); c->d_seed.alloc(16);
   CUDA_CHECK(cudaMemset(c->d_step.p, 0, 16));
@@ -545,12 +548,18 @@ void decode_step(gstvd_ctx* c, const DecodeGeom& g, const gstvd_gen_params& gp, 
   PdlScope pdl_scope(!(c->cfg.flags & GSTVD_FLAG_NO_PDL));
   const int H = c->H, M = g.B * g.K;
   const int* d_step = (const int*)c->d_step.p;
+  // Beam mode with the lean self-attention kernel: the cache is never gathered, the kernel reads each history position from the
+  // slot recorded in the ancestry table (EXPERIMENTAL, env GSTVD_SELF_ANC=1)
+  const char* anc_env = getenv("GSTVD_SELF_ANC");
+  const bool use_anc = gp.mode == GSTVD_SELECT_BEAM && anc_env != nullptr && atoi(anc_env) != 0 &&
+                       dec_self_attn_v2_active(c->dtype, g, c->dqkv.p, c->self_cache.p, c->dctx.p);
+  const uint8_t* anc = use_anc ? (const uint8_t*)c->anc.p : nullptr;
   c->launches += launch_embed_step(c->dtype, M, H, (const int32_t*)c->cur_tokens.p, d_step, c->word, c->pos, c->type,
                                    c->emb_ln.g, c->emb_ln.b, c->dh.p, s);
   for (int l = 0; l < c->dec_layers; ++l) {
     const DecLayer& L = c->d_layers[l];
     X.gemm(c->dh.p, H, L.qkv, c->dqkv.p, 3 * H, M);
-    c->launches += launch_dec_self_attn(c->dtype, g, l, c->dqkv.p, c->self_cache.p, d_step, c->dctx.p, s);
+    c->launches += launch_dec_self_attn(c->dtype, g, l, c->dqkv.p, c->self_cache.p, d_step, anc, c->dctx.p, s);
     X.gemm_add_ln(c->dctx.p, H, L.o, c->dh.p, L.ln_att, c->dtmp.p, c->da.p, M);
     X.gemm(c->da.p, H, L.cq, c->dqc.p, H, M);
     if (dec_cross_tma_supported(c->dtype, g))
@@ -570,7 +579,8 @@ void decode_step(gstvd_ctx* c, const DecodeGeom& g, const gstvd_gen_params& gp, 
                                      nullptr, 0, nsel, sv, si, nullptr, s);
     BeamBuffers bb = beam_buffers(c);
     c->launches += launch_beam_step(bb, g.B, g.K, g.T, c->V, nsel, sv, si, 102, nullptr, nullptr, nullptr, s);
-    c->launches += launch_reorder_cache(c->dtype, g, c->self_cache.p, bb.beam_idx, d_step, 0, nullptr, s);
+    if (use_anc) c->launches += launch_anc_update(g, bb.beam_idx, d_step, (uint8_t*)c->anc.p, s);
+    else c->launches += launch_reorder_cache(c->dtype, g, c->self_cache.p, bb.beam_idx, d_step, 0, nullptr, s);
   } else {
     const int nsel = kSelMax;
     const int32_t* bt = nullptr; const int32_t* bc = nullptr;
@@ -807,7 +817,7 @@ void gstvd_destroy(gstvd_ctx* c) {
                     &c->tmp_v, &c->ffn_t, &c->ffn_v, &c->feat_cast, &c->fused, &c->pool, &c->fused_mask, &c->dh, &c->da, &c->db, &c->dqkv,
                     &c->dctx, &c->dtmp, &c->dffn, &c->dqc, &c->logits, &c->cross_cache, &c->self_cache, &c->cross_len, &c->labels, &c->sel_val, &c->sel_idx,
                     &c->logz, &c->ban_tokens, &c->ban_count, &c->prefix, &c->seq, &c->beam_scores, &c->beam_tokens, &c->cur_tokens,
-                    &c->beam_idx, &c->beam_done, &c->hyp_score, &c->hyp_len, &c->hyp_tokens, &c->hyp_count, &c->hyp_worst, &c->d_step, &c->d_seed};
+                    &c->beam_idx, &c->beam_done, &c->hyp_score, &c->hyp_len, &c->hyp_tokens, &c->hyp_count, &c->hyp_worst, &c->d_step, &c->d_seed, &c->anc};
   for (DevBuf* b : bufs) b->release();
   for (auto& r : c->prof_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (c->ev_in) cudaEventDestroy(c->ev_in);

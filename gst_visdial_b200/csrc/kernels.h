@@ -118,7 +118,12 @@ struct DecodeGeom {
 // self-attention for one new position per row: appends k/v at position *d_step and attends over 0..*d_step
 // qkv [M, 3H]; cache layout [layer][kv][b][t][k][H]
 int launch_dec_self_attn(int dtype, const DecodeGeom& g, int layer, const void* qkv, void* self_cache, const int* d_step,
-                         void* out, cudaStream_t stream);
+                         const uint8_t* anc, void* out, cudaStream_t stream);
+// the lean bf16 / 64-dim kernel will run for these arguments (default on; env GSTVD_SELF_V2=0 disables it)
+bool dec_self_attn_v2_active(int dtype, const DecodeGeom& g, const void* qkv, const void* self_cache, const void* out);
+// anc: uint8 [B*K][32] ancestry table (slot that holds position t of beam k's history), permuted instead of gathering the cache;
+// only the lean kernel reads it - pass null to the self-attention and call launch_reorder_cache otherwise
+int launch_anc_update(const DecodeGeom& g, const int32_t* beam_idx, const int* d_step, uint8_t* anc, cudaStream_t stream);
 // cross-attention of every beam row over its image's cross K/V. cross layout [layer][b][kv*heads+h][Le][D]
 int launch_dec_cross_attn(int dtype, const DecodeGeom& g, int layer, const void* q, const void* cross_cache,
                           const float* enc_mask, void* out, cudaStream_t stream);
