@@ -52,6 +52,33 @@ def test_linear_tcgen05_bf16(eng, M, N, K, act):
     assert err < 2e-3, f"tcgen05 GEMM {M}x{N}x{K} act={act}: max abs err {err}, rel rms {rel_rms(y, ref)}"
 
 
+def _ref_linear_add_ln(a, w, b, r, gamma, beta):
+    """Reference of the fused GEMM + residual + LayerNorm cluster kernel (opt-in on the decode path, GSTVD_FUSE_LN): the unfused
+    pair it replaces - bf16 GEMM output (fp32 accumulate), then LN(x + residual) in fp32, bf16 result."""
+    a, w, r = a.bfloat16().double(), w.bfloat16().double(), r.bfloat16().double()
+    x = (a @ w.t() + b.double()).float().bfloat16().double()
+    z = x + r
+    mean = z.mean(-1, keepdim=True)
+    var = ((z - mean) ** 2).mean(-1, keepdim=True)
+    return (gamma.double() * ((z - mean) / torch.sqrt(var + 1e-12)) + beta.double()).float()
+
+
+@pytest.mark.parametrize("cluster", [16, 8])
+@pytest.mark.parametrize("M,K", [(320, 768), (320, 3072), (64, 768), (37, 768), (300, 3072), (1, 256), (129, 1024)])
+def test_linear_add_layernorm_cluster(eng, M, K, cluster):
+    g = torch.Generator().manual_seed(M * 13 + K + cluster)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(768, K, generator=g) / math.sqrt(K)
+    b = torch.randn(768, generator=g)
+    r = torch.randn(M, 768, generator=g)
+    gamma, beta = torch.randn(768, generator=g), torch.randn(768, generator=g)
+    y = eng.op_linear_add_layernorm(a, w, b, r, gamma, beta, cluster=cluster).cpu()
+    ref = _ref_linear_add_ln(a, w, b, r, gamma, beta)
+    # bf16 output: half an ulp at |y| <= 4 is 1.6e-2; a bf16 rounding flip of x moves y by about as much
+    err = max_abs(y, ref)
+    assert err < 5e-2 and rel_rms(y, ref) < 5e-3, f"fused GEMM+LN M={M} K={K} cluster={cluster}: max abs {err}, rel rms {rel_rms(y, ref)}"
+
+
 @pytest.mark.parametrize("M,N,K", [(37, 1024, 2048), (300, 768, 768), (64, 3072, 768), (5, 2, 1024), (129, 40, 72), (33, 1000, 128)])
 @pytest.mark.parametrize("act", [0, 1])
 def test_linear_simt_fp32(eng, M, N, K, act):
