@@ -844,10 +844,13 @@ void launch_cfg(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
 // Pipeline per CTA (one tile, not persistent): warp 0 = TMA producer (A: 64 rows x 256 k, W: BN rows x 256 k per stage, 3-D
 // boxes of four 128-byte-swizzled k-chunks), warp 1 = tcgen05.mma issuer (M = 64, N = BN), warps 2-5 = epilogue (one per TMEM
 // lane quadrant; the M = 64 accumulator keeps rows in lanes 0-15 of each quadrant).
-template <int CL, int BN> struct LnTileCfg {
+template <int CL, int BN, int CK = 4> struct LnTileCfg {
   static constexpr int kBM = 64;
-  static constexpr int kCK = 4;
+  static constexpr int kCK = CK;                               // k-chunks (64 elements) per ring stage
   static constexpr int kStages = BN <= 48 ? 3 : 2;
+  // CK = 2: 95 KB per CTA instead of 182 KB, so that two CTAs (this kernel's, or another stream's GEMM) share an SM - the 182 KB
+  // configuration lost 6 % dialogs/s with three streams in flight although it won single-stream
+  static constexpr int kCtasPerSm = CK <= 2 && BN <= 48 ? 2 : 1;
   static constexpr int kAChunk = kBM * BK * 2;
   static constexpr int kBChunk = BN * BK * 2;
   static constexpr int kABytes = kAChunk * kCK;
@@ -861,6 +864,7 @@ template <int CL, int BN> struct LnTileCfg {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "BN: multiple of 16 (tcgen05.ld x16 blocks, UMMA N % 8)");
   static_assert(kBChunk % 1024 == 0, "each k-chunk of the W tile must start on a swizzle-atom boundary");
   static_assert(kSmemBytes <= 232448, "shared memory budget");
+  static_assert(kCtasPerSm == 1 || 2 * (kSmemBytes + 1024) <= 233472, "two CTAs per SM must fit");
 };
 
 struct GemmLnArgs {
@@ -903,10 +907,10 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <int CL, int BN>
-__global__ void __launch_bounds__(6 * 32, 1)
+template <int CL, int BN, int CK>
+__global__ void __launch_bounds__(6 * 32, LnTileCfg<CL, BN, CK>::kCtasPerSm)
 gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmLnArgs p) {
-  using Cfg = LnTileCfg<CL, BN>;
+  using Cfg = LnTileCfg<CL, BN, CK>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kCK = Cfg::kCK;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -930,7 +934,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
   const uint32_t rank = cluster_ctarank();             // column tile of this CTA (cluster spans gridDim.x == CL)
   const int m_blk = blockIdx.y;
   const int n0 = (int)rank * BN;
-  const int num_kb = p.K / (BK * kCK);                 // host guarantees K % 256 == 0
+  const int num_kb = p.K / (BK * kCK);                 // host guarantees K % 256 == 0 (a multiple of every BK * kCK in use)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -1092,13 +1096,13 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
   }
 }
 
-template <int CL, int BN>
+template <int CL, int BN, int CK>
 void launch_ln_cfg(const GemmArgs& a, const GemmLnArgs& p, cudaStream_t stream) {
-  using Cfg = LnTileCfg<CL, BN>;
+  using Cfg = LnTileCfg<CL, BN, CK>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_ln_cluster_kernel<CL, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e == cudaSuccess && CL > 8) e = cudaFuncSetAttribute(gemm_ln_cluster_kernel<CL, BN>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaError_t e = cudaFuncSetAttribute(gemm_ln_cluster_kernel<CL, BN, CK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e == cudaSuccess && CL > 8) e = cudaFuncSetAttribute(gemm_ln_cluster_kernel<CL, BN, CK>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) throw std::runtime_error(std::string("gemm_ln: cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     attr_set = true;
   }
@@ -1115,7 +1119,7 @@ void launch_ln_cfg(const GemmArgs& a, const GemmLnArgs& p, cudaStream_t stream) 
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_flag() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_ln_cluster_kernel<CL, BN>, ma, mb, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_ln_cluster_kernel<CL, BN, CK>, ma, mb, p);
   if (e != cudaSuccess) throw std::runtime_error(std::string("gemm_ln: launch failed: ") + cudaGetErrorString(e));
 }
 
@@ -1443,8 +1447,11 @@ int launch_gemm_ln_tc(const GemmArgs& a, const void* res, int64_t ldr, const flo
   p.Y = reinterpret_cast<bf16*>(Y); p.ldy = ldy; p.M = a.M; p.N = a.N; p.K = a.K; p.eps = eps;
   static const bool exact_sum = getenv("GSTVD_FUSE_LN_NO_ROUND") != nullptr;   // keep the fp32 GEMM result instead of mirroring the bf16 round trip
   p.round_bf16 = exact_sum ? 0 : 1;
-  if (cluster == 8) launch_ln_cfg<8, 96>(a, p, stream);
-  else launch_ln_cfg<16, 48>(a, p, stream);
+  const char* small_env = getenv("GSTVD_FUSE_LN_SMALL");      // read per launch: 95 KB configuration (two CTAs per SM), not yet run on a GPU
+  const bool small = small_env != nullptr && atoi(small_env) != 0;
+  if (cluster == 8) launch_ln_cfg<8, 96, 4>(a, p, stream);
+  else if (small) launch_ln_cfg<16, 48, 2>(a, p, stream);
+  else launch_ln_cfg<16, 48, 4>(a, p, stream);
   return 1;
 }
 

@@ -86,3 +86,21 @@ def test_encoder_pair_gemm_matches_single(full_cfgs, full_sd):
     finally:
         os.environ.pop("GSTVD_GEMM_2CTA", None)
         e.close()
+
+
+@pytest.mark.parametrize("M,K", [(320, 768), (320, 3072), (37, 768), (129, 1024)])
+def test_linear_add_layernorm_small_footprint(eng, M, K):
+    """The 95 KB configuration of the fused GEMM + LayerNorm cluster kernel (two k-chunks per ring stage, two CTAs per SM) gives
+    the same bits as the validated 182 KB configuration: same products in the same k order, same statistics exchange."""
+    g = torch.Generator().manual_seed(M * 13 + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(768, K, generator=g) / math.sqrt(K)
+    b, r = torch.randn(768, generator=g), torch.randn(M, 768, generator=g)
+    gamma, beta = torch.randn(768, generator=g), torch.randn(768, generator=g)
+    y_big = eng.op_linear_add_layernorm(a, w, b, r, gamma, beta, cluster=16).cpu()
+    os.environ["GSTVD_FUSE_LN_SMALL"] = "1"
+    try:
+        y_small = eng.op_linear_add_layernorm(a, w, b, r, gamma, beta, cluster=16).cpu()
+    finally:
+        os.environ.pop("GSTVD_FUSE_LN_SMALL", None)
+    assert torch.equal(y_small, y_big), max_abs(y_small, y_big)
