@@ -121,6 +121,8 @@ struct gstvd_ctx {
   std::vector<ProfRec> prof_pool; size_t prof_used = 0;
   cudaStream_t own_stream = nullptr;     // decode steps run (and are graph-captured) here: the caller may be on the legacy stream
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaStream_t side_stream = nullptr;    // image stream of the encoder when it runs beside the text stream (GSTVD_ENC_FORK)
+  cudaEvent_t ev_main = nullptr, ev_side = nullptr;
 
   size_t act_bytes(size_t elems) const { return elems * esz; }
 };
@@ -404,27 +406,34 @@ void self_layer_fwd(Exec& X, const SelfLayer& L, void* x, void* y, void* qkv, vo
   (void)c;
 }
 
-void conn_layer_fwd(Exec& X, const ConnLayer& L, int B, int Lt, int Lv, const float* tmask, const float* vmask) {
-  gstvd_ctx* c = X.c;
+// XT runs the text-stream work, XV the image-stream work.  They are the same Exec unless the encoder is forked over two CUDA
+// streams (do_encode); `exchange` then orders the two streams against each other around the co-attention pair: both attentions
+// read BOTH streams' q|k|v buffers, and neither stream may overwrite its buffer (next layer's projection) while the other's
+// attention still reads it.
+template <typename Exchange>
+void conn_layer_fwd(Exec& XT, Exec& XV, const ConnLayer& L, int B, int Lt, int Lv, const float* tmask, const float* vmask, Exchange&& exchange) {
+  gstvd_ctx* c = XT.c;
   const int H = c->H, Hv = c->Hv, Hb = c->Hb, D = Hb / c->heads_b, Mt = B * Lt, Mv = B * Lv;
   void *xt = c->xt.p, *yt = c->yt.p, *xv = c->xv.p, *yv = c->yv.p;
   void *qv = c->qkv_v.p, *qt = c->qkv_t.p;
-  X.gemm(xv, Hv, L.qkv1, qv, 3 * Hb, Mv);      // query1 | key1 | value1  (image stream)
-  X.gemm(xt, H, L.qkv2, qt, 3 * Hb, Mt);       // query2 | key2 | value2  (text stream)
+  XV.gemm(xv, Hv, L.qkv1, qv, 3 * Hb, Mv);      // query1 | key1 | value1  (image stream)
+  XT.gemm(xt, H, L.qkv2, qt, 3 * Hb, Mt);       // query2 | key2 | value2  (text stream)
+  exchange();
   // text queries over image keys/values -> ctx_t ; image queries over text keys/values -> ctx_v  (:671-710)
-  X.attention(qt, 3 * Hb, Lt, X.off(qv, Hb), X.off(qv, 2 * Hb), 3 * Hb, Lv, c->ctx_t.p, Hb, B, c->heads_b, D, vmask, -10000.0f, 0);
-  X.attention(qv, 3 * Hb, Lv, X.off(qt, Hb), X.off(qt, 2 * Hb), 3 * Hb, Lt, c->ctx_v.p, Hb, B, c->heads_b, D, tmask, -10000.0f, 0);
+  XT.attention(qt, 3 * Hb, Lt, XT.off(qv, Hb), XT.off(qv, 2 * Hb), 3 * Hb, Lv, c->ctx_t.p, Hb, B, c->heads_b, D, vmask, -10000.0f, 0);
+  XV.attention(qv, 3 * Hb, Lv, XV.off(qt, Hb), XV.off(qt, 2 * Hb), 3 * Hb, Lt, c->ctx_v.p, Hb, B, c->heads_b, D, tmask, -10000.0f, 0);
+  exchange();
   // BertBiOutput with the contexts swapped into the opposite stream (:765, :732-744)
-  X.gemm(c->ctx_v.p, Hb, L.dense1, c->tmp_v.p, Hv, Mv);
-  X.add_ln(c->tmp_v.p, xv, L.ln1, yv, Mv);
-  X.gemm(c->ctx_t.p, Hb, L.dense2, c->tmp_t.p, H, Mt);
-  X.add_ln(c->tmp_t.p, xt, L.ln2, yt, Mt);
-  X.gemm(yv, Hv, L.v_f1, c->ffn_v.p, c->Fv, Mv, 1);
-  X.gemm(c->ffn_v.p, c->Fv, L.v_f2, c->tmp_v.p, Hv, Mv);
-  X.add_ln(c->tmp_v.p, yv, L.v_ln, xv, Mv);
-  X.gemm(yt, H, L.t_f1, c->ffn_t.p, c->F, Mt, 1);
-  X.gemm(c->ffn_t.p, c->F, L.t_f2, c->tmp_t.p, H, Mt);
-  X.add_ln(c->tmp_t.p, yt, L.t_ln, xt, Mt);
+  XV.gemm(c->ctx_v.p, Hb, L.dense1, c->tmp_v.p, Hv, Mv);
+  XV.add_ln(c->tmp_v.p, xv, L.ln1, yv, Mv);
+  XT.gemm(c->ctx_t.p, Hb, L.dense2, c->tmp_t.p, H, Mt);
+  XT.add_ln(c->tmp_t.p, xt, L.ln2, yt, Mt);
+  XV.gemm(yv, Hv, L.v_f1, c->ffn_v.p, c->Fv, Mv, 1);
+  XV.gemm(c->ffn_v.p, c->Fv, L.v_f2, c->tmp_v.p, Hv, Mv);
+  XV.add_ln(c->tmp_v.p, yv, L.v_ln, xv, Mv);
+  XT.gemm(yt, H, L.t_f1, c->ffn_t.p, c->F, Mt, 1);
+  XT.gemm(c->ffn_t.p, c->F, L.t_f2, c->tmp_t.p, H, Mt);
+  XT.add_ln(c->tmp_t.p, yt, L.t_ln, xt, Mt);
 }
 
 void check_ready(gstvd_ctx* c) { if (!c->finalized) throw StateError("weights not finalized: call gstvd_finalize_weights first"); }
@@ -448,29 +457,44 @@ void do_encode(gstvd_ctx* c, int B, int Lt, int Lv, const int64_t* ids, const in
   PdlScope pdl_scope(!(c->cfg.flags & GSTVD_FLAG_NO_PDL));
   if (Lt > c->cfg.max_position_embeddings) throw InvalidArg("encode: Lt exceeds max_position_embeddings");
   Exec X{c, s};
+  // The two streams of the ViLBERT encoder only meet in the co-attention of a connection layer (models/vilbert_dialog.py:831-905):
+  // with GSTVD_ENC_FORK=1 the image stream (2 368 rows at batch 64: half a wave of GEMM tiles) runs on a second CUDA stream beside
+  // the text stream and fills the SMs its wave tails leave idle.  EXPERIMENTAL (host-side change only, same kernels): not yet timed.
+  const char* fork_env = getenv("GSTVD_ENC_FORK");
+  const bool fork = fork_env != nullptr && atoi(fork_env) != 0 && c->side_stream != nullptr && s != c->side_stream;
+  Exec XV{c, fork ? c->side_stream : s};
+  auto exchange = [&] {                       // each stream waits for everything the other has enqueued so far
+    if (!fork) return;
+    CUDA_CHECK(cudaEventRecord(c->ev_main, s));
+    CUDA_CHECK(cudaEventRecord(c->ev_side, c->side_stream));
+    CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_side, 0));
+    CUDA_CHECK(cudaStreamWaitEvent(c->side_stream, c->ev_main, 0));
+  };
+  exchange();                                 // fork: the side stream starts after whatever precedes this call on `s`
   const int H = c->H, Hv = c->Hv, Mt = B * Lt, Mv = B * Lv;
   c->launches += launch_embed_text(c->dtype, Mt, Lt, H, ids, seg, nullptr, 0, c->word, c->pos, c->type, c->type_ext,
                                    c->cfg.type_vocab_size, c->emb_ln.g, c->emb_ln.b, c->xt.p, s);
   const void* feat_in = feat;
   if (c->dtype != kF32) {
-    c->launches += launch_cast_f32_to(c->dtype, feat, c->feat_cast.p, (int64_t)Mv * c->cfg.v_feature_size, s);
+    c->launches += launch_cast_f32_to(c->dtype, feat, c->feat_cast.p, (int64_t)Mv * c->cfg.v_feature_size, XV.s);
     feat_in = c->feat_cast.p;
   }
-  X.gemm(feat_in, c->cfg.v_feature_size, c->img_emb, c->tmp_v.p, Hv, Mv);
-  c->launches += launch_image_embed_ln(c->dtype, Mv, Hv, c->tmp_v.p, loc, c->loc_w, c->loc_b, c->img_ln.g, c->img_ln.b, c->xv.p, s);
+  XV.gemm(feat_in, c->cfg.v_feature_size, c->img_emb, c->tmp_v.p, Hv, Mv);
+  c->launches += launch_image_embed_ln(c->dtype, Mv, Hv, c->tmp_v.p, loc, c->loc_w, c->loc_b, c->img_ln.g, c->img_ln.b, c->xv.p, XV.s);
 
   auto text_layer = [&](int i) { self_layer_fwd(X, c->t_layers[i], c->xt.p, c->yt.p, c->qkv_t.p, c->ctx_t.p, c->tmp_t.p, c->ffn_t.p, B, Lt, c->heads, att); };
-  auto image_layer = [&](int i) { self_layer_fwd(X, c->v_layers[i], c->xv.p, c->yv.p, c->qkv_v.p, c->ctx_v.p, c->tmp_v.p, c->ffn_v.p, B, Lv, c->heads_v, imask); };
+  auto image_layer = [&](int i) { self_layer_fwd(XV, c->v_layers[i], c->xv.p, c->yv.p, c->qkv_v.p, c->ctx_v.p, c->tmp_v.p, c->ffn_v.p, B, Lv, c->heads_v, imask); };
   int v_start = 0, t_start = 0;
   for (int n = 0; n < c->cfg.num_connections; ++n) {          // models/vilbert_dialog.py:831-905
     const int v_end = c->cfg.v_biattention_id[n], t_end = c->cfg.t_biattention_id[n];
     for (int i = v_start; i < v_end; ++i) image_layer(i);
     for (int i = t_start; i < t_end; ++i) text_layer(i);
-    conn_layer_fwd(X, c->c_layers[n], B, Lt, Lv, att, imask);
+    conn_layer_fwd(X, XV, c->c_layers[n], B, Lt, Lv, att, imask, exchange);
     v_start = v_end; t_start = t_end;
   }
   for (int i = v_start; i < c->cfg.v_num_hidden_layers; ++i) image_layer(i);
   for (int i = t_start; i < c->cfg.num_hidden_layers; ++i) text_layer(i);
+  exchange();                                 // join: everything below reads both streams' results on `s`
 
   if (out_t) c->launches += launch_cast_to_f32(c->dtype, c->xt.p, out_t, (int64_t)Mt * H, s);
   if (out_v) c->launches += launch_cast_to_f32(c->dtype, c->xv.p, out_v, (int64_t)Mv * Hv, s);
@@ -800,6 +824,9 @@ int gstvd_create(const gstvd_config* cfg, int device, gstvd_ctx** out) {
     CUDA_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
     CUDA_CHECK(cudaDeviceSynchronize());
   });
   if (rc != GSTVD_OK) { if (c) gstvd_destroy(c); return rc; }
@@ -823,6 +850,9 @@ void gstvd_destroy(gstvd_ctx* c) {
   if (c->ev_in) cudaEventDestroy(c->ev_in);
   if (c->ev_out) cudaEventDestroy(c->ev_out);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->ev_main) cudaEventDestroy(c->ev_main);
+  if (c->ev_side) cudaEventDestroy(c->ev_side);
+  if (c->side_stream) cudaStreamDestroy(c->side_stream);
   delete c;
   if (prev >= 0) cudaSetDevice(prev);
 }

@@ -104,3 +104,32 @@ def test_linear_add_layernorm_small_footprint(eng, M, K):
     finally:
         os.environ.pop("GSTVD_FUSE_LN_SMALL", None)
     assert torch.equal(y_small, y_big), max_abs(y_small, y_big)
+
+
+@pytest.mark.parametrize("which", ["tiny", "full"])
+def test_forked_encoder_is_identical(full_cfgs, full_sd, tiny_cfgs, tiny_sd, which):
+    """GSTVD_ENC_FORK=1: image stream of the encoder on a second CUDA stream beside the text stream (host-side scheduling only, the
+    same kernels on the same buffers): every output must be bit-identical, call after call (a missing cross-stream dependency
+    shows up as a difference or as run-to-run noise)."""
+    from gst_visdial_b200.engine import Engine
+    enc_cfg, dec_cfg = full_cfgs if which == "full" else tiny_cfgs
+    B = 8
+    e = Engine(enc_cfg, dec_cfg, dtype="bf16", max_batch=B, max_beams=5)
+    e.load_state_dict(full_sd if which == "full" else tiny_sd)
+    try:
+        b = history_batch(enc_cfg, 0, B)
+
+        def run():
+            o = e.encode(b["enc_input_ids"], b["enc_image_feat"], b["enc_image_loc"], b["enc_segments"], b["enc_att_mask"],
+                         b["enc_image_mask"], want_t=True, want_v=True, want_fused=True)
+            return o["seq_t"].cpu(), o["seq_v"].cpu(), o["fused"].cpu()
+
+        ref = run()
+        os.environ["GSTVD_ENC_FORK"] = "1"
+        for _ in range(5):
+            got = run()
+            for x, y in zip(got, ref):
+                assert torch.equal(x, y), max_abs(x, y)
+    finally:
+        os.environ.pop("GSTVD_ENC_FORK", None)
+        e.close()
