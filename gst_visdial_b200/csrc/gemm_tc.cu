@@ -51,7 +51,7 @@ template <int BN, int EW> struct TileCfg {
   // bound by the RATE of TMA operations issued by one thread (~0.13 us each), not by bytes: one 3-D box
   // {64, rows, chunks} moves several k-blocks per operation.
   static constexpr int kCK = kSkinny ? (BN <= 32 ? 4 : 2) : (BN <= 64 ? 4 : 1);
-  static constexpr int kStages = kSkinny ? (BN <= 32 ? 2 : 3) : (BN == 256 ? 4 : (BN == 128 ? 6 : 2));
+  static constexpr int kStages = kSkinny ? (BN <= 32 ? 2 : (BN <= 64 ? 3 : 2)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 2));
   static constexpr int kAChunk = kBM * BK * 2;                 // one kBM-row x 64-element SW128 tile
   static constexpr int kBChunk = BN * BK * 2;
   static constexpr int kABytes = kAChunk * kCK;
@@ -660,6 +660,15 @@ int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream, bool 
                            getenv("GSTVD_GEMM_NO_TMA_STORE") == nullptr;
     if (skinny && direct_ok && a.K % BK == 0 && !bn_env) {
       const int tm64 = (a.M + 63) / 64;
+      // A/B aid (read per launch): GSTVD_GEMM_SKINNY_BN=64|128 widens the decode tiles.  The 32-column tiles are the fastest for one
+      // stream (most CTAs, least per-CTA bytes) but every one of the N/32 column tiles re-reads the 64 x K activation block through
+      // L2: 17.7 MB per 768 x 768 GEMM against 11.8 MB (64 columns) / 8.8 MB (128 columns) - and with several streams in flight
+      // the L2 -> SM fabric is the contended resource.  Not yet timed.
+      if (const char* wenv = getenv("GSTVD_GEMM_SKINNY_BN")) {
+        const int w = atoi(wenv);
+        if (w == 128) { launch_cfg<128, kEpiWarpsSkinny>(a, num_sms, stream); return 1; }
+        if (w == 64) { launch_cfg<64, kEpiWarpsSkinny>(a, num_sms, stream); return 1; }
+      }
       static const int multi = [] { const char* e = getenv("GSTVD_GEMM_SKINNY_WAVES"); return e ? atoi(e) : 1; }();   // A/B aid
       if (tm64 * ((a.N + 31) / 32) <= 2 * num_sms * multi) { launch_cfg<32, kEpiWarpsSkinny>(a, num_sms, stream); return 1; }
       // wider outputs (N = 2304 / 3072 at M = 320) measured faster in the 128-row configuration with 16 epilogue warps

@@ -133,3 +133,21 @@ def test_forked_encoder_is_identical(full_cfgs, full_sd, tiny_cfgs, tiny_sd, whi
     finally:
         os.environ.pop("GSTVD_ENC_FORK", None)
         e.close()
+
+
+@pytest.mark.parametrize("bn", ["64", "128"])
+@pytest.mark.parametrize("M,N,K", [(320, 768, 768), (320, 768, 3072), (320, 2304, 768), (320, 3072, 768), (37, 768, 768), (300, 1000, 256)])
+def test_linear_skinny_tile_width(eng, M, N, K, bn):
+    """GSTVD_GEMM_SKINNY_BN: wider 64-row decode tiles (fewer re-reads of the activation block through L2); same kernel template as
+    the default 32-column tiles, so the results must be bit-identical to them."""
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g)
+    y0 = eng.op_linear(a, w, b, act=1, dtype="bf16").cpu()
+    os.environ["GSTVD_GEMM_SKINNY_BN"] = bn
+    try:
+        y1 = eng.op_linear(a, w, b, act=1, dtype="bf16").cpu()
+    finally:
+        os.environ.pop("GSTVD_GEMM_SKINNY_BN", None)
+    assert torch.equal(y1, y0), max_abs(y1, y0)
