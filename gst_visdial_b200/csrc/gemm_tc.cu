@@ -664,6 +664,13 @@ int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream, bool 
       // stream (most CTAs, least per-CTA bytes) but every one of the N/32 column tiles re-reads the 64 x K activation block through
       // L2: 17.7 MB per 768 x 768 GEMM against 11.8 MB (64 columns) / 8.8 MB (128 columns) - and with several streams in flight
       // the L2 -> SM fabric is the contended resource.  Not yet timed.
+      // GSTVD_GEMM_WIDE_BN=128|256 (N > 768 only: the QKV and FFN1 projections): 128-row tiles of that width instead of 64 columns -
+      // three row blocks re-read W instead of five, and half / a quarter as many column tiles re-read the activations
+      // (31.8 -> 21.2 MB for N = 2304, 42 -> 28.3 MB for N = 3072 at 128 columns).  Not yet timed.
+      if (const char* wide = getenv("GSTVD_GEMM_WIDE_BN")) {
+        const int w = atoi(wide);
+        if (a.N > 768 && (w == 128 || w == 256)) { if (w == 128) launch_cfg<128>(a, num_sms, stream); else launch_cfg<256>(a, num_sms, stream); return 1; }
+      }
       if (const char* wenv = getenv("GSTVD_GEMM_SKINNY_BN")) {
         const int w = atoi(wenv);
         if (w == 128) { launch_cfg<128, kEpiWarpsSkinny>(a, num_sms, stream); return 1; }

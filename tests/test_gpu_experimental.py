@@ -151,3 +151,21 @@ def test_linear_skinny_tile_width(eng, M, N, K, bn):
     finally:
         os.environ.pop("GSTVD_GEMM_SKINNY_BN", None)
     assert torch.equal(y1, y0), max_abs(y1, y0)
+
+
+@pytest.mark.parametrize("bn", ["128", "256"])
+@pytest.mark.parametrize("M,N,K", [(320, 2304, 768), (320, 3072, 768), (300, 30522, 768)])
+def test_linear_wide_decode_tiles(eng, M, N, K, bn):
+    """GSTVD_GEMM_WIDE_BN: the N > 768 decode projections on 128-row tiles of 128 / 256 columns (validated configurations of the
+    throughput kernel applied to a skinny problem): bit-identical to the default tiling."""
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g)
+    y0 = eng.op_linear(a, w, b, act=0, dtype="bf16").cpu()
+    os.environ["GSTVD_GEMM_WIDE_BN"] = bn
+    try:
+        y1 = eng.op_linear(a, w, b, act=0, dtype="bf16").cpu()
+    finally:
+        os.environ.pop("GSTVD_GEMM_WIDE_BN", None)
+    assert torch.equal(y1, y0), max_abs(y1, y0)
