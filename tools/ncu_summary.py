@@ -22,6 +22,12 @@ WANT = [
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
     ("smsp__inst_executed.sum", "warp instructions"),
     ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64 pipe active %"),
+    # L2 -> SM traffic (the budget the streams share).  `--set full` carries the lts__t_* counters.
+    ("lts__t_bytes.sum", "L2 bytes (all traffic)"), ("lts__t_bytes.sum.per_second", "L2 byte rate"),
+    ("lts__t_sectors_srcunit_tex_op_read.sum", "L2 sectors read by SMs (x 32 B)"),
+    ("lts__t_sector_hit_rate.pct", "L2 hit rate %"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 throughput % of ncu peak"),
+    ("l1tex__m_xbar2l1tex_read_bytes.sum", "crossbar -> SM read bytes"),
 ]
 
 for rep in sys.argv[1:]:
