@@ -18,5 +18,10 @@ case "${1:-validate}" in
       env $cfg timeout 120 python bench.py --steps 4 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1
       env $cfg timeout 60 python tools/profile_round.py --hist 150 2>&1 | tail -2
     done | tee gpurun_out/r2_ab.log
+    # streams in flight with the default kernels (3 was the optimum before the late round-1 kernels)
+    for n in 2 4; do
+      echo "== --streams $n"
+      timeout 120 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --streams $n 2>/dev/null | tail -1
+    done | tee -a gpurun_out/r2_ab.log
     ;;
 esac
