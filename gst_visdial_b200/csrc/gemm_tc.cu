@@ -622,6 +622,7 @@ int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream, bool 
   if (a.K % 8 != 0) throw std::runtime_error("gemm_tc: K must be a multiple of 8");
   if (a.hm_D > 0 && (a.hm_D % 32 != 0)) throw std::runtime_error("gemm_tc: head-major scatter needs head_dim % 32 == 0");
   gemm_tc_init();
+  if (launch_gemm_splitk_if_selected(a, stream)) return 1;         // EXPERIMENTAL cluster split-K kernel for decode problems (env GSTVD_GEMM_SPLITK)
   if (launch_gemm_tc2_if_selected(a, num_sms, stream)) return 1;   // EXPERIMENTAL CTA-pair kernel (env GSTVD_GEMM_2CTA)
   const int tiles_m = (a.M + BM - 1) / BM;
   int bn = 32;

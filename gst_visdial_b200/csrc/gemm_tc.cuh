@@ -301,6 +301,8 @@ const CUtensorMap& get_map_c(const void* ptr, int64_t rows, int64_t cols, int64_
 
 // CTA-pair kernel (gemm_tc2.cu): launches it and returns 1 when env GSTVD_GEMM_2CTA selects it for this problem, else returns 0.
 int launch_gemm_tc2_if_selected(const GemmArgs& a, int num_sms, cudaStream_t stream);
+// Cluster split-K kernel for the decode projections (gemm_splitk.cu): same contract with env GSTVD_GEMM_SPLITK.
+int launch_gemm_splitk_if_selected(const GemmArgs& a, cudaStream_t stream);
 
 }  // namespace tc
 }  // namespace gstvd
