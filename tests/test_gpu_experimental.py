@@ -55,12 +55,13 @@ def test_linear_pair_bf16(eng, M, N, K, act, bn):
         y2 = eng.op_linear(a, w, b, act=act, dtype="bf16").cpu()
     finally:
         os.environ.pop("GSTVD_GEMM_2CTA", None)
-    a64, w64 = a.bfloat16().double(), w.bfloat16().double()
-    ref = a64 @ w64.t() + b.double()
-    if act:
-        ref = ref * 0.5 * (1.0 + torch.erf(ref / math.sqrt(2.0)))
-    err = max_abs(y2, ref.float())
-    assert err < 2e-3, f"pair GEMM {M}x{N}x{K} act={act} bn={bn}: max abs err {err}, rel rms {rel_rms(y2, ref.float())}"
+    if M * N * K < 4e9:                                  # the fp64 reference on the host is slow; the single-CTA kernel is the main oracle
+        a64, w64 = a.bfloat16().double(), w.bfloat16().double()
+        ref = a64 @ w64.t() + b.double()
+        if act:
+            ref = ref * 0.5 * (1.0 + torch.erf(ref / math.sqrt(2.0)))
+        err = max_abs(y2, ref.float())
+        assert err < 2e-3, f"pair GEMM {M}x{N}x{K} act={act} bn={bn}: max abs err {err}, rel rms {rel_rms(y2, ref.float())}"
     # same products, same k order, fp32 accumulation in the tensor core: expected to be bit-identical to the single-CTA kernel
     assert max_abs(y2, y1) < 1e-5, f"pair vs single-CTA kernel: {max_abs(y2, y1)}"
 
