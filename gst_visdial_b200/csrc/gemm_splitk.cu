@@ -220,10 +220,10 @@ gemm_splitk_cluster_kernel(const __grid_constant__ CUtensorMap tm_a, const __gri
 
 // The problems this kernel takes: decode-step projections (few rows, whole 128-column tiles, whole k-ranges per split, plain
 // row-major output with 16-byte aligned rows and bias).
-bool splitk_eligible(const GemmArgs& a) {
+bool splitk_eligible(const GemmArgs& a, int max_rows) {
   const int esz = a.out_f32 ? 4 : 2;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  return a.hm_D == 0 && a.M >= 1 && a.M <= 4 * BM && a.N >= kSkBN && a.N % kSkBN == 0 && a.N <= 4096 && a.K % (kSplit * BK) == 0 &&
+  return a.hm_D == 0 && a.M >= 1 && a.M <= max_rows && a.N >= kSkBN && a.N % kSkBN == 0 && a.N <= 4096 && a.K % (kSplit * BK) == 0 &&
          al16(a.A) && al16(a.W) && al16(a.C) && (a.bias == nullptr || al16(a.bias)) && a.lda % 8 == 0 && a.ldw % 8 == 0 &&
          (a.ldc * esz) % 16 == 0;
 }
@@ -234,7 +234,10 @@ namespace tc {
 
 int launch_gemm_splitk_if_selected(const GemmArgs& a, cudaStream_t stream) {
   const char* env = getenv("GSTVD_GEMM_SPLITK");             // read per launch
-  if (env == nullptr || atoi(env) == 0 || !splitk_eligible(a)) return 0;
+  // 1: the decode problems (M <= 512).  2: also the half-wave problems of the encoder's image stream (M <= 4096: 2 368 rows at batch
+  // 64 are 76 single-CTA tiles on 148 SMs; split over K they are 600 CTAs)
+  const int mode = env ? atoi(env) : 0;
+  if (mode == 0 || !splitk_eligible(a, mode >= 2 ? 4096 : 4 * BM)) return 0;
   gemm_tc_init();
   static bool attr_set = false;
   if (!attr_set) {

@@ -172,7 +172,7 @@ def test_linear_wide_decode_tiles(eng, M, N, K, bn):
     assert torch.equal(y1, y0), max_abs(y1, y0)
 
 
-SPLITK_SHAPES = [(320, 768, 768), (320, 768, 3072), (320, 2304, 768), (320, 3072, 768), (64, 768, 768), (37, 768, 1024), (300, 1024, 256),
+SPLITK_SHAPES = [(2368, 1024, 1024), (2368, 3072, 1024), (320, 768, 768), (320, 768, 3072), (320, 2304, 768), (320, 3072, 768), (64, 768, 768), (37, 768, 1024), (300, 1024, 256),
                  (1, 128, 256), (512, 256, 512)]
 
 
@@ -185,7 +185,7 @@ def test_linear_cluster_splitk(eng, M, N, K, act):
     a = torch.randn(M, K, generator=g)
     w = torch.randn(N, K, generator=g) / math.sqrt(K)
     b = torch.randn(N, generator=g)
-    os.environ["GSTVD_GEMM_SPLITK"] = "1"
+    os.environ["GSTVD_GEMM_SPLITK"] = "2" if M > 512 else "1"
     try:
         y = eng.op_linear(a, w, b, act=act, dtype="bf16").cpu()
         y_again = eng.op_linear(a, w, b, act=act, dtype="bf16").cpu()
