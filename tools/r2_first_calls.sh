@@ -7,9 +7,17 @@ set -u
 mkdir -p gpurun_out
 case "${1:-validate}" in
   validate)
-    # CTA-pair GEMM (tcgen05 cta_group::2): op-level parity on ragged shapes + whole-encoder comparison; own process, own timeout
-    GSTVD_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_gpu_experimental.py -m gpu -x -q -s > gpurun_out/r2_experimental.log 2>&1
-    tail -25 gpurun_out/r2_experimental.log
+    # One pytest process per kernel family: a device-side trap poisons the CUDA context of its process only, and every family gets
+    # its own verdict.  (CTA-pair GEMM, 95 KB GEMM+LN, forked encoder, decode tile widths, cluster split-K.)
+    : > gpurun_out/r2_experimental.log
+    for fam in "test_linear_pair_bf16" "test_encoder_pair_gemm" "test_linear_add_layernorm_small_footprint" "test_forked_encoder" \
+               "test_linear_skinny_tile_width" "test_linear_wide_decode_tiles" "test_linear_cluster_splitk" "test_decode_with_cluster_splitk"; do
+      echo "===== $fam" | tee -a gpurun_out/r2_experimental.log
+      GSTVD_EXPERIMENTAL=1 timeout 240 python -m pytest tests/test_gpu_experimental.py -m gpu -x -q -s -k "$fam" >> gpurun_out/r2_experimental.log 2>&1
+      echo "$fam: exit $?" | tee -a gpurun_out/r2_verdicts.log
+    done
+    cat gpurun_out/r2_verdicts.log
+    grep -E "passed|failed|Error|error" gpurun_out/r2_experimental.log | tail -30
     ;;
   ab)
     # same-box A/B of every opt-in switch on the bench workload (3 streams) and on one single-stream round
