@@ -51,3 +51,31 @@ def test_beam1_equals_greedy(tiny_cfgs, tiny_sd):
         s, _ = beam.beam_search(tiny_sd, enc_cfg, dec_cfg, b, num_beams=1)
     if not (g == beam.EOS).any():
         assert torch.equal(g, s)
+
+
+def test_ancestry_table_equals_cache_gather():
+    """The rule the bf16 beam path uses instead of `_reorder_cache` (visual_dialog_decoder.py:177-181; csrc/decode.cu
+    anc_update_kernel + dec_self_attn_v2_kernel): beams never move their cache slots; position t of beam k's history is read from
+    slot anc[k][t], and after a selection with parents p the rows become anc'[k][t] = anc[p[k]][t] (t < step), anc'[k][step] = p[k].
+    Restated here on integers against the plain gather, including repeated parents."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    for K, T in ((5, 18), (2, 7), (8, 32), (1, 4)):
+        gathered = np.zeros((T, K), dtype=np.int64)          # [position][beam]: what index_select leaves in the cache
+        slots = np.zeros((T, K), dtype=np.int64)             # [position][slot]: never moved
+        anc = np.zeros((K, 32), dtype=np.int64)
+        for step in range(T):
+            new = rng.integers(1, 1 << 30, size=K)           # what each beam writes at this position
+            gathered[step] = new
+            slots[step] = new
+            # what the self-attention of beam k reads at this step
+            for k in range(K):
+                hist = [slots[t, anc[k, t]] for t in range(step)] + [slots[step, k]]
+                assert hist == list(gathered[: step + 1, k])
+            parent = rng.integers(0, K, size=K)              # beam_idx of the step (not a permutation)
+            gathered[: step + 1] = gathered[: step + 1][:, parent]
+            new_anc = anc.copy()
+            for k in range(K):
+                new_anc[k, :step] = anc[parent[k], :step]
+                new_anc[k, step] = parent[k]
+            anc = new_anc
