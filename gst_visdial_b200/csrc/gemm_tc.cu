@@ -512,9 +512,6 @@ const CUtensorMap& get_map_c(const void* ptr, int64_t rows, int64_t cols, int64_
                     box_cols * esz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
-}  // namespace tc
-
-namespace {
 
 // Head-major cross-KV output [layers*B][G][L][D] bf16 (GemmArgs::hm_*): box = D x 128 positions of one (layer-image, group).
 // Activations of the head-major mode viewed as [B][L][K]: box = 64 k x 128 positions of one image (rows past L are zero-filled).
@@ -535,6 +532,11 @@ const CUtensorMap& get_map_hm3(const void* ptr, int D, int L, int64_t LBG, int b
   return cached_map(key, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, gdim, gstride, box,
                     box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
+
+}  // namespace tc
+
+namespace {
+
 const CUtensorMap& get_map_hm(const void* ptr, int D, int L, int G, int64_t LB) {
   MapKey key{ptr, L, D, D, BM, D, 2, 2, G, LB};
   cuuint64_t gdim[4] = {(cuuint64_t)D, (cuuint64_t)L, (cuuint64_t)G, (cuuint64_t)LB};

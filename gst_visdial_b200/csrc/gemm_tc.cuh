@@ -299,6 +299,11 @@ const CUtensorMap& get_map_k3(const void* ptr, int64_t rows, int64_t cols, int64
 // Output map for the TMA-store epilogue: [M, N] row-major with box = box_cols x 128 rows.
 const CUtensorMap& get_map_c(const void* ptr, int64_t rows, int64_t cols, int64_t ld, int esz, int box_cols);
 
+// Head-major mode (cross-attention K/V prefill, GemmArgs::hm_*): activations viewed as [B][L][K] (box = 64 k x 128 positions of one
+// image, rows past L zero-filled) and the output [layers*B*G][L][D] (box = box_cols x 128 positions of one (layer-image, group)).
+const CUtensorMap& get_map_a3(const void* ptr, int64_t K, int L, int B, int64_t ld);
+const CUtensorMap& get_map_hm3(const void* ptr, int D, int L, int64_t LBG, int box_cols);
+
 // CTA-pair kernel (gemm_tc2.cu): launches it and returns 1 when env GSTVD_GEMM_2CTA selects it for this problem, else returns 0.
 int launch_gemm_tc2_if_selected(const GemmArgs& a, int num_sms, cudaStream_t stream);
 // Cluster split-K kernel for the decode projections (gemm_splitk.cu): same contract with env GSTVD_GEMM_SPLITK.

@@ -56,6 +56,12 @@ __device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* ma
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(leader_bar)
       : "memory");
 }
+__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(leader_bar)
+      : "memory");
+}
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");
@@ -114,7 +120,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int tiles_n = (p.N + BN - 1) / BN;
-  const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
+  // 128-row units: CTA `rank` of pair tile m_blk works on unit 2 * m_blk + rank.  In the head-major (prefill) mode a unit never
+  // straddles two images (hm_tpi units per image, the rows past hm_L are zero-filled on load and clipped on store).
+  const int units = p.hm_tpi > 0 ? p.hm_B * p.hm_tpi : (p.M + BM - 1) / BM;
+  const int tiles_m = (units + 1) / 2;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (p.K + BK - 1) / BK;
 
@@ -146,7 +155,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         tma2_load_2d(b_base + st * Cfg::kBBytes, &tm_b, kb * BK, n_blk * BN + (int)rank * Cfg::kBH, full_bar(st) & kPeerBitMask);
       };
       auto load_a = [&](int st, int kb, int m_blk) {
-        tma2_load_2d(a_base + st * Cfg::kABytes, &tm_a, kb * BK, m_blk * 2 * BM + (int)rank * BM, full_bar(st) & kPeerBitMask);
+        const int u = m_blk * 2 + (int)rank;
+        if (p.hm_tpi > 0) {
+          const int img = u / p.hm_tpi;                   // a unit past the last image is out of bounds in the third coordinate: zeros
+          tma2_load_3d(a_base + st * Cfg::kABytes, &tm_a, kb * BK, (u - img * p.hm_tpi) * BM, img, full_bar(st) & kPeerBitMask);
+        } else {
+          tma2_load_2d(a_base + st * Cfg::kABytes, &tm_a, kb * BK, u * BM, full_bar(st) & kPeerBitMask);
+        }
       };
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
@@ -210,11 +225,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const int tile_row0 = m_blk * 2 * BM + (int)rank * BM;
+      const int unit = m_blk * 2 + (int)rank;
+      const int tile_row0 = unit * BM;
       const int r = quad * 32 + lane;
       const bool issuer = (e & 3) == 0 && lane == 0;
       const uint32_t tq = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-      if (tile_row0 < p.M) {                            // block-uniform: a pair tile whose lower half is past M has nothing to store
+      if (p.hm_tpi > 0 ? unit < units : tile_row0 < p.M) {   // block-uniform: the second half of the last pair tile may not exist
         if (p.out_f32) {
           if (grp < 2) {
             const uint32_t stg = stage_base + grp * 16384;
@@ -260,11 +276,15 @@ void launch_cfg2(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
   }
   GemmArgs a = a_in;
   const int esz = a.out_f32 ? 4 : 2;
-  const CUtensorMap& ma = get_map(a.A, a.M, a.K, a.lda, BM);
+  const bool hm = a.hm_D > 0;                                 // head-major prefill mode (pick_pair_bn has checked its preconditions)
+  a.tma_store = 1;
+  a.hm_tpi = hm ? (a.hm_L + BM - 1) / BM : 0;
+  const CUtensorMap& ma = hm ? get_map_a3(a.A, a.K, a.hm_L, a.hm_B, a.lda) : get_map(a.A, a.M, a.K, a.lda, BM);
   const CUtensorMap& mb = get_map(a.W, a.N, a.K, a.ldw, Cfg::kBH);
-  const CUtensorMap& mc = get_map_c(a.C, a.M, a.N, a.ldc, esz, 32);
-  a.tma_store = 1; a.hm_tpi = 0;
-  const int tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * ((a.N + BN - 1) / BN);
+  const CUtensorMap& mc = hm ? get_map_hm3(a.C, a.hm_D, a.hm_L, (int64_t)(a.N / (a.hm_D * a.hm_G)) * a.hm_B * a.hm_G, 32)
+                             : get_map_c(a.C, a.M, a.N, a.ldc, esz, 32);
+  const int units = hm ? a.hm_B * a.hm_tpi : (a.M + BM - 1) / BM;
+  const int tiles = ((units + 1) / 2) * ((a.N + BN - 1) / BN);
   const int pairs = std::min(tiles, num_sms / 2);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(Cfg::kThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = stream;
@@ -283,9 +303,17 @@ int pick_pair_bn(const GemmArgs& a, int num_sms) {
   const char* env = getenv("GSTVD_GEMM_2CTA");
   if (env == nullptr || atoi(env) == 0) return 0;
   const int esz = a.out_f32 ? 4 : 2;
-  if (a.hm_D != 0 || a.M < 8 * BM || a.N < 128 || a.K % 8 != 0 || (reinterpret_cast<uintptr_t>(a.C) & 15) != 0 || (a.ldc * esz) % 16 != 0 ||
-      getenv("GSTVD_GEMM_NO_TMA_STORE") != nullptr)
+  if (a.M < 8 * BM || a.N < 128 || a.K % 8 != 0 || (reinterpret_cast<uintptr_t>(a.C) & 15) != 0 || getenv("GSTVD_GEMM_NO_TMA_STORE") != nullptr)
     return 0;
+  if (a.hm_D != 0) {
+    // head-major (cross-K/V prefill) output: its own switch until the plain mode has been validated
+    const char* hm_env = getenv("GSTVD_GEMM_2CTA_HM");
+    if (hm_env == nullptr || atoi(hm_env) == 0 || a.out_f32 || a.hm_D % 32 != 0 || a.M != a.hm_B * a.hm_L || a.N % (a.hm_D * a.hm_G) != 0 ||
+        getenv("GSTVD_GEMM_NO_TMA_HM") != nullptr)
+      return 0;
+  } else if ((a.ldc * esz) % 16 != 0) {
+    return 0;
+  }
   const int forced = atoi(env);
   if (forced == 128 || forced == 256) return forced;
   // the width that fills the 74 pairs best (a 128-column pair tile runs the tensor pipe at ~0.85 of the 256-column one)

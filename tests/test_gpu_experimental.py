@@ -223,3 +223,28 @@ def test_decode_with_cluster_splitk_agrees(full_cfgs, full_sd):
     finally:
         os.environ.pop("GSTVD_GEMM_SPLITK", None)
         e.close()
+
+
+def test_prefill_pair_gemm_head_major(full_cfgs, full_sd):
+    """Cross-K/V prefill (head-major TMA-store epilogue, 3-D activation map) through the CTA-pair kernel: the decode that reads the
+    cache must produce the same tokens as with the single-CTA prefill (the GEMM results are expected to be bit-identical)."""
+    from gst_visdial_b200.engine import Engine
+    enc_cfg, dec_cfg = full_cfgs
+    B = 8
+    e = Engine(enc_cfg, dec_cfg, dtype="bf16", max_batch=B, max_beams=5)
+    e.load_state_dict(full_sd)
+    try:
+        b = history_batch(enc_cfg, 0, B)
+        o = e.encode(b["enc_input_ids"], b["enc_image_feat"], b["enc_image_loc"], b["enc_segments"], b["enc_att_mask"], b["enc_image_mask"])
+        res = []
+        for flags in ({}, {"GSTVD_GEMM_2CTA": "1", "GSTVD_GEMM_2CTA_HM": "1"}):
+            os.environ.update(flags)
+            try:
+                e.prefill_cross(B, o["Le"])
+            finally:
+                for k in flags:
+                    os.environ.pop(k, None)
+            res.append((e.generate(B, num_beams=1, top_k=1).cpu(), e.generate(B, num_beams=5).cpu()))
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    finally:
+        e.close()

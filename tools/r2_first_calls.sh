@@ -10,7 +10,7 @@ case "${1:-validate}" in
     # One pytest process per kernel family: a device-side trap poisons the CUDA context of its process only, and every family gets
     # its own verdict.  (CTA-pair GEMM, 95 KB GEMM+LN, forked encoder, decode tile widths, cluster split-K.)
     : > gpurun_out/r2_experimental.log
-    for fam in "test_linear_pair_bf16" "test_encoder_pair_gemm" "test_linear_add_layernorm_small_footprint" "test_forked_encoder" \
+    for fam in "test_linear_pair_bf16" "test_encoder_pair_gemm" "test_prefill_pair_gemm_head_major" "test_linear_add_layernorm_small_footprint" "test_forked_encoder" \
                "test_linear_skinny_tile_width" "test_linear_wide_decode_tiles" "test_linear_cluster_splitk" "test_decode_with_cluster_splitk"; do
       echo "===== $fam" | tee -a gpurun_out/r2_experimental.log
       GSTVD_EXPERIMENTAL=1 timeout 240 python -m pytest tests/test_gpu_experimental.py -m gpu -x -q -s -k "$fam" >> gpurun_out/r2_experimental.log 2>&1
@@ -21,7 +21,7 @@ case "${1:-validate}" in
     ;;
   ab)
     # same-box A/B of every opt-in switch on the bench workload (3 streams) and on one single-stream round
-    for cfg in "X=0" "GSTVD_GEMM_2CTA=1" "GSTVD_GEMM_2CTA=256" "GSTVD_FUSE_LN=16" "GSTVD_FUSE_LN=16 GSTVD_FUSE_LN_SMALL=1" "GSTVD_GEMM_SPLITK=1" "GSTVD_GEMM_SPLITK=2" "GSTVD_GEMM_SKINNY_BN=64" "GSTVD_GEMM_SKINNY_BN=128" "GSTVD_GEMM_SKINNY_BN=64 GSTVD_GEMM_WIDE_BN=128" "GSTVD_GEMM_WIDE_BN=128" "GSTVD_ENC_FORK=1" "GSTVD_SELF_ANC=0" "GSTVD_SELF_V2=0 GSTVD_SELF_ANC=0"; do
+    for cfg in "X=0" "GSTVD_GEMM_2CTA=1" "GSTVD_GEMM_2CTA=256" "GSTVD_GEMM_2CTA=1 GSTVD_GEMM_2CTA_HM=1" "GSTVD_FUSE_LN=16" "GSTVD_FUSE_LN=16 GSTVD_FUSE_LN_SMALL=1" "GSTVD_GEMM_SPLITK=1" "GSTVD_GEMM_SPLITK=2" "GSTVD_GEMM_SKINNY_BN=64" "GSTVD_GEMM_SKINNY_BN=128" "GSTVD_GEMM_SKINNY_BN=64 GSTVD_GEMM_WIDE_BN=128" "GSTVD_GEMM_WIDE_BN=128" "GSTVD_ENC_FORK=1" "GSTVD_SELF_ANC=0" "GSTVD_SELF_V2=0 GSTVD_SELF_ANC=0"; do
       echo "== $cfg"
       env $cfg timeout 120 python bench.py --steps 4 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1
       env $cfg timeout 60 python tools/profile_round.py --hist 150 2>&1 | tail -2
