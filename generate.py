@@ -100,16 +100,31 @@ def main(argv=None):
     # every finished batch is appended to this rank's JSON-lines file by a writer thread (gst_visdial_b200/io/output.py)
     final = os.path.join(params['save_path'], params['save_name'])
     part = f"{final}.rank{rank}.jsonl"
-    with torch.no_grad(), IOO.JsonlWriter(part) as writer:
-        for batch in batches():
-            res = generate_dialogs(a_model, batch, q_model=q_model, num_rounds=params['num_rounds'], a_kwargs=a_kwargs, q_kwargs=q_kwargs,
-                                   with_ppl=True, device=params['device'])
-            meta = {int(i): {"url": "", "caption": (decode or ids_to_text)(IOO.strip_ids(row) if decode else row)}
-                    for i, row in zip(batch["image_id"].tolist(), batch["enc_input_ids"].tolist())}
-            writer.write(IOO.batch_records(batch["image_id"], res.questions, res.answers, res.answer_ppl, res.abnormal,
-                                           decode=decode or ids_to_text, meta=meta))
+    # A failing rank must not leave the others hanging in the barrier, and rank 0 must not merge partial files: every rank
+    # reports a status flag (one all_reduce) before the merge and all of them raise if any failed.
+    failure = None
+    try:
+        with torch.no_grad(), IOO.JsonlWriter(part) as writer:
+            for (span_start, _), batch in zip(spans, batches()):
+                # sampling keyed by (-seed, model role, round, GLOBAL image index, step): the tokens of an image do not depend on the
+                # batch size or on how many ranks share the job
+                res = generate_dialogs(a_model, batch, q_model=q_model, num_rounds=params['num_rounds'], a_kwargs=a_kwargs, q_kwargs=q_kwargs,
+                                       with_ppl=True, device=params['device'], seed=params.get('seed', 0), row_offset=span_start)
+                meta = {int(i): {"url": "", "caption": (decode or ids_to_text)(IOO.strip_ids(row) if decode else row)}
+                        for i, row in zip(batch["image_id"].tolist(), batch["enc_input_ids"].tolist())}
+                writer.write(IOO.batch_records(batch["image_id"], res.questions, res.answers, res.answer_ppl, res.abnormal,
+                                               decode=decode or ids_to_text, meta=meta))
+    except Exception as e:                                                   # noqa: BLE001 - reported to every rank below
+        failure = e
     if world > 1:
-        torch.distributed.barrier()
+        flag = torch.tensor([1 if failure is not None else 0], device=params['device'])
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX)
+        if int(flag.item()) and failure is None:
+            failure = RuntimeError("another rank failed while generating; no output was merged")
+    if failure is not None:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        raise failure
     if rank == 0:
         merged = f"{final}.jsonl"
         with open(merged, "w") as dst:

@@ -157,7 +157,7 @@ dec_self_attn_kernel(DecodeGeom g, int layer, const T* __restrict__ qkv, T* __re
 template <int NIT>
 __global__ void __launch_bounds__(128)
 dec_self_attn_v2_kernel(DecodeGeom g, int layer, const bf16* __restrict__ qkv, bf16* __restrict__ cache, const int* __restrict__ d_step,
-                        const uint8_t* __restrict__ anc, bf16* __restrict__ out) {
+                        int step_host, const uint8_t* __restrict__ anc, bf16* __restrict__ out) {
   pdl_wait();
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -171,7 +171,10 @@ dec_self_attn_v2_kernel(DecodeGeom g, int layer, const bf16* __restrict__ qkv, b
   const uint4 q_raw = *reinterpret_cast<const uint4*>(qrow);
   const uint4 kn_raw = *reinterpret_cast<const uint4*>(qrow + H);
   const uint4 vn_raw = *reinterpret_cast<const uint4*>(qrow + 2 * H);
-  const int step = *d_step;
+  // step_host >= 0: the launch knows the step (eager loops and the all-steps graph unroll them), so the loads below are bounded by
+  // it - on average half of the g.T cache rows - without waiting for *d_step; otherwise every row is requested and masked afterwards
+  const int step = step_host >= 0 ? step_host : *d_step;
+  const int bound = step_host >= 0 ? step_host : g.T;          // cache positions < bound are requested
   // element offset of (kv, position t) for this beam / head / chunk
   const int64_t pos_stride = (int64_t)g.K * H;
   const int64_t k_base = ((((int64_t)layer * 2 + 0) * g.B + b) * g.T) * pos_stride + h * 64 + chunk * 8;   // slot 0 of position 0
@@ -183,15 +186,19 @@ dec_self_attn_v2_kernel(DecodeGeom g, int layer, const bf16* __restrict__ qkv, b
 #pragma unroll
   for (int it = 0; it < NIT; ++it) {
     const int t = it * 4 + grp;
-    slot[it] = anc != nullptr ? min((int)anc[((int64_t)b * g.K + kb) * kMaxSteps + (t & (kMaxSteps - 1))], g.K - 1) : kb;
+    slot[it] = (anc != nullptr && t < bound) ? min((int)anc[((int64_t)b * g.K + kb) * kMaxSteps + (t & (kMaxSteps - 1))], g.K - 1) : kb;
   }
   uint4 k_raw[NIT], v_raw[NIT];
 #pragma unroll
   for (int it = 0; it < NIT; ++it) {
     const int t = it * 4 + grp;
-    const int tc = t < g.T ? t : 0;                  // rows past the cache capacity: any valid address, masked below
-    k_raw[it] = *reinterpret_cast<const uint4*>(cache + k_base + tc * pos_stride + (int64_t)slot[it] * H);
-    v_raw[it] = *reinterpret_cast<const uint4*>(cache + v_base + tc * pos_stride + (int64_t)slot[it] * H);
+    if (t < bound && t < g.T) {                      // rows at or past the bound are never used (t == step comes from qkv, t > step is masked)
+      k_raw[it] = *reinterpret_cast<const uint4*>(cache + k_base + t * pos_stride + (int64_t)slot[it] * H);
+      v_raw[it] = *reinterpret_cast<const uint4*>(cache + v_base + t * pos_stride + (int64_t)slot[it] * H);
+    } else {
+      k_raw[it] = make_uint4(0, 0, 0, 0);
+      v_raw[it] = make_uint4(0, 0, 0, 0);
+    }
   }
   // append the new position (lanes 0-7: key chunks, lanes 8-15: value chunks)
   if (grp == 0) *reinterpret_cast<uint4*>(cache + k_base + step * pos_stride + (int64_t)kb * H) = kn_raw;
@@ -647,15 +654,15 @@ int launch_anc_update(const DecodeGeom& g, const int32_t* beam_idx, const int* d
   return 1;
 }
 
-int launch_dec_self_attn(int dtype, const DecodeGeom& g, int layer, const void* qkv, void* self_cache, const int* d_step,
+int launch_dec_self_attn(int dtype, const DecodeGeom& g, int layer, const void* qkv, void* self_cache, const int* d_step, int step_host,
                          const uint8_t* anc, void* out, cudaStream_t stream) {
   if (g.D != 64 && g.D != 128) throw std::runtime_error("dec_self_attn: head_dim must be 64 or 128");
   if (g.T > kMaxSteps) throw std::runtime_error("dec_self_attn: at most 32 cached positions");
   dim3 grid(g.B * g.K, (g.heads + 3) / 4);
   // lean variant: bf16, 64-dim heads, 16-byte aligned rows
   if (dec_self_attn_v2_active(dtype, g, qkv, self_cache, out)) {
-    if (g.T <= 20) launch_k(dec_self_attn_v2_kernel<5>, grid, dim3(128), 0, stream, g, layer, (const bf16*)qkv, (bf16*)self_cache, d_step, anc, (bf16*)out);
-    else launch_k(dec_self_attn_v2_kernel<8>, grid, dim3(128), 0, stream, g, layer, (const bf16*)qkv, (bf16*)self_cache, d_step, anc, (bf16*)out);
+    if (g.T <= 20) launch_k(dec_self_attn_v2_kernel<5>, grid, dim3(128), 0, stream, g, layer, (const bf16*)qkv, (bf16*)self_cache, d_step, step_host, anc, (bf16*)out);
+    else launch_k(dec_self_attn_v2_kernel<8>, grid, dim3(128), 0, stream, g, layer, (const bf16*)qkv, (bf16*)self_cache, d_step, step_host, anc, (bf16*)out);
     return 1;
   }
   if (anc != nullptr) throw std::runtime_error("dec_self_attn: the ancestry table is only read by the bf16 / 64-dim kernel");

@@ -54,7 +54,10 @@ struct Linear { int out = 0, in = 0; float* w32 = nullptr; float* b = nullptr; b
 struct LNp { int n = 0; float* g = nullptr; float* b = nullptr; };
 struct SelfLayer { Linear qkv, o, f1, f2; LNp ln_att, ln_out; };
 struct ConnLayer { Linear qkv1, qkv2, dense1, dense2, v_f1, v_f2, t_f1, t_f2; LNp ln1, ln2, v_ln, t_ln; };
-struct DecLayer { Linear qkv, o, cq, co, f1, f2; LNp ln_att, ln_cross, ln_out; };
+// Deferred LayerNorm (bf16 decode step): a projection whose input is LN(x) multiplies the RAW x by W' = W * gamma instead;
+// c / d are the epilogue's correction vectors (GemmArgs::fold_*, launch_fold_ln_weights).
+struct FoldLin { int out = 0, in = 0; bf16* w16 = nullptr; float* c = nullptr; float* d = nullptr; };
+struct DecLayer { Linear qkv, o, cq, co, f1, f2; LNp ln_att, ln_cross, ln_out; FoldLin qkv_f, cq_f, f1_f; };
 struct Slot { float* dst; int64_t numel; bool loaded; };
 
 struct DevBuf {
@@ -108,6 +111,10 @@ struct gstvd_ctx {
   DevBuf beam_scores, beam_tokens, cur_tokens, beam_idx, beam_done, hyp_score, hyp_len, hyp_tokens, hyp_count, hyp_worst;
   DevBuf d_step, d_seed;
   DevBuf anc;                                         // uint8 [B*K][32]: beam ancestry table (launch_anc_update)
+  DevBuf fold16, foldvec;                             // deferred LayerNorm: folded bf16 weights, c / d vectors
+  DevBuf st1, st2, st3;                               // float2 [rows][kLnStatStride]: partial row statistics of the raw x1 / x2 / x3
+  bool fold_ready = false;
+  int64_t stats_ld = 0;                               // row capacity of st1 / st2 / st3 (layout [part][row])
   int enc_B = 0, enc_Le = 0;        // shape of the resident fused states
   int cross_B = 0, cross_Le = 0;    // shape of the resident cross K/V
   // beam op-test state
@@ -322,6 +329,8 @@ void alloc_workspace(gstvd_ctx* c) {
     c->hyp_worst.alloc(B * 8);
     c->anc.alloc(B * K * 32);
     CUDA_CHECK(cudaMemset(c->anc.p, 0, B * K * 32));
+    c->stats_ld = (int64_t)((R + 15) & ~size_t(15));
+    c->st1.alloc(c->stats_ld * kLnStatStride * 8); c->st2.alloc(c->stats_ld * kLnStatStride * 8); c->st3.alloc(c->stats_ld * kLnStatStride * 8);
   }
   c->d_step.alloc(16); c->d_seed.alloc(16);
   CUDA_CHECK(cudaMemset(c->d_step.p, 0, 16));
@@ -355,6 +364,20 @@ struct Exec {
         }
       }
     }
+  }
+  // Deferred-LayerNorm GEMM (bf16 decode step): C = act(LN?(A) W^T + b + LN?(res)) stored raw, with optional statistics out.
+  //   fold != null : A holds RAW rows whose partial statistics are a_stats (GemmArgs::fold_*), the weights are fold's
+  //   res_ln != null : the residual is LN(res) with that layer norm's affine and the partial statistics res_stats
+  void gemm_ln(const void* A, int64_t lda, const Linear& L, const FoldLin* fold, const float2* a_stats, void* C, int M, int act,
+               const void* res, const LNp* res_ln, const float2* res_stats, float2* stats_out) {
+    GemmArgs a;
+    a.A = A; a.lda = lda; a.ldw = L.in; a.C = C; a.ldc = L.out; a.act = act; a.M = M; a.N = L.out; a.K = L.in;
+    if (fold) { a.W = fold->w16; a.bias = fold->d; a.fold_c = fold->c; a.fold_stats = a_stats; a.fold_parts = L.in / 32; }
+    else { a.W = L.w16; a.bias = L.b; }
+    a.res = res; a.ldr = L.out;
+    if (res_ln) { a.res_stats = res_stats; a.res_parts = L.out / 32; a.res_gamma = res_ln->g; a.res_beta = res_ln->b; }
+    a.stats_out = stats_out; a.stats_ld = c->stats_ld;
+    c->launches += launch_gemm_tc(a, c->num_sms, s);
   }
   void add_ln(const void* x, const void* res, const LNp& l, void* y, int rows) {
     c->launches += launch_add_layernorm(dt(), rows, l.n, x, l.n, res, l.n, l.g, l.b, y, l.n, s);
@@ -434,6 +457,29 @@ void conn_layer_fwd(Exec& XT, Exec& XV, const ConnLayer& L, int B, int Lt, int L
   XT.gemm(yt, H, L.t_f1, c->ffn_t.p, c->F, Mt, 1);
   XT.gemm(c->ffn_t.p, c->F, L.t_f2, c->tmp_t.p, H, Mt);
   XT.add_ln(c->tmp_t.p, yt, L.t_ln, xt, Mt);
+}
+
+// Deferred LayerNorm weights of the decoder (bf16 contexts): per layer cq' = cq * gamma(ln_att), f1' = f1 * gamma(ln_cross) and,
+// from layer 1 on, qkv' = qkv * gamma(ln_out of the layer below), each with its c / d vectors.  113 MB at the reference geometry.
+void prepare_fold(gstvd_ctx* c, cudaStream_t s) {
+  c->fold_ready = false;
+  if (c->dtype != kBF16 || c->dec_layers == 0 || c->H % 64 != 0 || c->H > 32 * kLnStatStride) return;
+  const size_t H = c->H, F = c->dec_F;
+  const size_t per_layer_mat = (H + F + 3 * H) * H, per_layer_vec = 2 * (H + F + 3 * H);
+  if (!c->fold16.p) { c->fold16.alloc(per_layer_mat * c->dec_layers * 2); c->foldvec.alloc(per_layer_vec * c->dec_layers * 4); }
+  bf16* m = (bf16*)c->fold16.p; float* v = (float*)c->foldvec.p;
+  auto prep = [&](FoldLin& f, const Linear& L, const LNp& ln) {
+    f.out = L.out; f.in = L.in; f.w16 = m; f.c = v; f.d = v + L.out;
+    m += (size_t)L.out * L.in; v += 2 * (size_t)L.out;
+    c->launches += launch_fold_ln_weights(L.out, L.in, L.w32, ln.g, ln.b, L.b, f.w16, f.c, f.d, s);
+  };
+  for (int l = 0; l < c->dec_layers; ++l) {
+    DecLayer& L = c->d_layers[l];
+    prep(L.cq_f, L.cq, L.ln_att);
+    prep(L.f1_f, L.f1, L.ln_cross);
+    if (l > 0) prep(L.qkv_f, L.qkv, c->d_layers[l - 1].ln_out);
+  }
+  c->fold_ready = true;
 }
 
 void check_ready(gstvd_ctx* c) { if (!c->finalized) throw StateError("weights not finalized: call gstvd_finalize_weights first"); }
@@ -566,8 +612,10 @@ BeamBuffers beam_buffers(gstvd_ctx* c) {
 }
 
 // One decode step for all M = B*K rows: embeddings -> 12 x [self-attn over cache, cross-attn, FFN] -> LM head -> selection.
+// step_host = index of this step when the caller knows it (it always does: eager loops and the captured graph both unroll the
+// steps), so kernels that only need it to bound their loads take it as a launch parameter instead of reading *d_step first.
 void decode_step(gstvd_ctx* c, const DecodeGeom& g, const gstvd_gen_params& gp, const int64_t* hist_ids, const int64_t* hist_seg,
-                 int Lh, cudaStream_t s) {
+                 int Lh, cudaStream_t s, int step_host) {
   Exec X{c, s};
   PdlScope pdl_scope(!(c->cfg.flags & GSTVD_FLAG_NO_PDL));
   const int H = c->H, M = g.B * g.K;
@@ -580,10 +628,42 @@ void decode_step(gstvd_ctx* c, const DecodeGeom& g, const gstvd_gen_params& gp, 
   const uint8_t* anc = use_anc ? (const uint8_t*)c->anc.p : nullptr;
   c->launches += launch_embed_step(c->dtype, M, H, (const int32_t*)c->cur_tokens.p, d_step, c->word, c->pos, c->type,
                                    c->emb_ln.g, c->emb_ln.b, c->dh.p, s);
+  // Deferred LayerNorm (default for bf16): no LayerNorm kernel inside the layer stack - the three dense -> LN(x + input) pairs of a
+  // layer store raw sums + partial row statistics, their consumers normalise on the fly (GemmArgs::fold_* / res_*), and one
+  // ln_apply_stats launch materialises the last layer's output for the LM head.  36 launches and 36 dependent stages per step less.
+  static const bool defer_env = [] { const char* e = getenv("GSTVD_DEFER_LN"); return e == nullptr || atoi(e) != 0; }();
+  const bool defer = defer_env && c->fold_ready && c->dtype == kBF16 && !(c->cfg.flags & GSTVD_FLAG_DEBUG_SIMT_GEMM) && M <= 512 &&
+                     gemm_ln_mode() == 0;
+  if (defer) {
+    float2 *st1 = (float2*)c->st1.p, *st2 = (float2*)c->st2.p, *st3 = (float2*)c->st3.p;
+    void *x1 = c->da.p, *x2 = c->db.p, *x3 = c->dtmp.p;
+    for (int l = 0; l < c->dec_layers; ++l) {
+      const DecLayer& L = c->d_layers[l];
+      const LNp* ln_below = l > 0 ? &c->d_layers[l - 1].ln_out : nullptr;
+      // q|k|v from LN_out(x3 of the layer below) (layer 0: from the embedding output, already normalised)
+      if (l == 0) X.gemm(c->dh.p, H, L.qkv, c->dqkv.p, 3 * H, M);
+      else X.gemm_ln(x3, H, L.qkv, &L.qkv_f, st3, c->dqkv.p, M, 0, nullptr, nullptr, nullptr, nullptr);
+      c->launches += launch_dec_self_attn(c->dtype, g, l, c->dqkv.p, c->self_cache.p, d_step, step_host, anc, c->dctx.p, s);
+      // x1 = o(ctx) + input
+      X.gemm_ln(c->dctx.p, H, L.o, nullptr, nullptr, x1, M, 0, l == 0 ? c->dh.p : x3, ln_below, st3, st1);
+      X.gemm_ln(x1, H, L.cq, &L.cq_f, st1, c->dqc.p, M, 0, nullptr, nullptr, nullptr, nullptr);
+      if (dec_cross_tma_supported(c->dtype, g))
+        c->launches += launch_dec_cross_tma(g, l, c->dqc.p, c->cross_cache.p, (const float*)c->fused_mask.p, (const int*)c->cross_len.p, c->dctx.p,
+                                            c->num_sms, s);
+      else
+        c->launches += launch_dec_cross_attn(c->dtype, g, l, c->dqc.p, c->cross_cache.p, (const float*)c->fused_mask.p, c->dctx.p, s);
+      // x2 = co(ctx) + LN_att(x1);  ffn = gelu(f1(LN_cross(x2)));  x3 = f2(ffn) + LN_cross(x2)
+      X.gemm_ln(c->dctx.p, H, L.co, nullptr, nullptr, x2, M, 0, x1, &L.ln_att, st1, st2);
+      X.gemm_ln(x2, H, L.f1, &L.f1_f, st2, c->dffn.p, M, 1, nullptr, nullptr, nullptr, nullptr);
+      X.gemm_ln(c->dffn.p, c->dec_F, L.f2, nullptr, nullptr, x3, M, 0, x2, &L.ln_cross, st2, st3);
+    }
+    c->launches += launch_ln_apply_stats(M, H, x3, st3, c->stats_ld, H / 32, c->d_layers[c->dec_layers - 1].ln_out.g, c->d_layers[c->dec_layers - 1].ln_out.b,
+                                         c->dh.p, s);
+  } else
   for (int l = 0; l < c->dec_layers; ++l) {
     const DecLayer& L = c->d_layers[l];
     X.gemm(c->dh.p, H, L.qkv, c->dqkv.p, 3 * H, M);
-    c->launches += launch_dec_self_attn(c->dtype, g, l, c->dqkv.p, c->self_cache.p, d_step, anc, c->dctx.p, s);
+    c->launches += launch_dec_self_attn(c->dtype, g, l, c->dqkv.p, c->self_cache.p, d_step, step_host, anc, c->dctx.p, s);
     X.gemm_add_ln(c->dctx.p, H, L.o, c->dh.p, L.ln_att, c->dtmp.p, c->da.p, M);
     X.gemm(c->da.p, H, L.cq, c->dqc.p, H, M);
     if (dec_cross_tma_supported(c->dtype, g))
@@ -615,7 +695,7 @@ void decode_step(gstvd_ctx* c, const DecodeGeom& g, const gstvd_gen_params& gp, 
     }
     c->launches += launch_row_select(M, c->V, (const float*)c->logits.p, c->Vpad, 1, nullptr, gp.temperature, bt, bc, Lh, nsel, sv, si,
                                      nullptr, s);
-    c->launches += launch_sample_step(M, g.T, nsel, sv, si, gp.top_k, gp.top_p, 0, (const uint64_t*)c->d_seed.p, d_step, 102, (int32_t*)c->seq.p,
+    c->launches += launch_sample_step(M, g.T, nsel, sv, si, gp.top_k, gp.top_p, 0, 0, (const uint64_t*)c->d_seed.p, d_step, 102, (int32_t*)c->seq.p,
                                       (int32_t*)c->cur_tokens.p, (int32_t*)c->prefix.p, g.T + 1, nullptr, s);
   }
   c->launches += launch_step_advance((int*)c->d_step.p, s);
@@ -643,13 +723,13 @@ void do_generate(gstvd_ctx* c, int B, const gstvd_gen_params& gp, const int64_t*
   }
   const DecodeGeom g = make_geom(c, B, K, T);
   // the sampling seed lives in device memory so that a captured graph can be replayed with a new seed
-  c->launches += launch_set_u64((uint64_t*)c->d_seed.p, gp.seed, s);
+  c->launches += launch_set_u64((uint64_t*)c->d_seed.p, gp.seed, (uint64_t)gp.row_offset, s);
   if (gp.mode == GSTVD_SELECT_BEAM) c->launches += launch_beam_init(beam_buffers(c), B, K, T, 101, s);
   else c->launches += launch_sample_init(B, T, 101, (int32_t*)c->seq.p, (int32_t*)c->cur_tokens.p, (int32_t*)c->prefix.p, T + 1, (int*)c->d_step.p, s);
 
   const bool use_graph = !(c->cfg.flags & GSTVD_FLAG_NO_CUDA_GRAPH);
   if (!use_graph) {
-    for (int t = 0; t < T; ++t) decode_step(c, g, gp, hist_ids, hist_seg, Lh, s);
+    for (int t = 0; t < T; ++t) decode_step(c, g, gp, hist_ids, hist_seg, Lh, s, t);
   } else {
     GraphKey key;
     std::memset(&key, 0, sizeof key);
@@ -664,7 +744,7 @@ void do_generate(gstvd_ctx* c, int B, const gstvd_gen_params& gp, const int64_t*
       cudaGraph_t graph;
       CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
       try {
-        for (int t = 0; t < T; ++t) decode_step(c, g, gp, hist_ids, hist_seg, Lh, s);   // all T steps in ONE graph: no host round trip between steps
+        for (int t = 0; t < T; ++t) decode_step(c, g, gp, hist_ids, hist_seg, Lh, s, t);   // all T steps in ONE graph: no host round trip between steps
       } catch (...) {
         cudaGraph_t dead; cudaStreamEndCapture(s, &dead);
         throw;
@@ -844,7 +924,8 @@ void gstvd_destroy(gstvd_ctx* c) {
                     &c->tmp_v, &c->ffn_t, &c->ffn_v, &c->feat_cast, &c->fused, &c->pool, &c->fused_mask, &c->dh, &c->da, &c->db, &c->dqkv,
                     &c->dctx, &c->dtmp, &c->dffn, &c->dqc, &c->logits, &c->cross_cache, &c->self_cache, &c->cross_len, &c->labels, &c->sel_val, &c->sel_idx,
                     &c->logz, &c->ban_tokens, &c->ban_count, &c->prefix, &c->seq, &c->beam_scores, &c->beam_tokens, &c->cur_tokens,
-                    &c->beam_idx, &c->beam_done, &c->hyp_score, &c->hyp_len, &c->hyp_tokens, &c->hyp_count, &c->hyp_worst, &c->d_step, &c->d_seed, &c->anc};
+                    &c->beam_idx, &c->beam_done, &c->hyp_score, &c->hyp_len, &c->hyp_tokens, &c->hyp_count, &c->hyp_worst, &c->d_step, &c->d_seed, &c->anc, &c->fold16, &c->foldvec,
+                    &c->st1, &c->st2, &c->st3};
   for (DevBuf* b : bufs) b->release();
   for (auto& r : c->prof_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (c->ev_in) cudaEventDestroy(c->ev_in);
@@ -889,6 +970,7 @@ int gstvd_finalize_weights(gstvd_ctx* c, void* stream) {
     if (c->dtype == kBF16) {
       c->launches += launch_cast_f32_to(kBF16, (const float*)c->mat32.p, c->mat16.p, (int64_t)c->mat_elems, s);
       assign_w16(c);
+      prepare_fold(c, s);
     }
     for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
     c->graphs.clear();
@@ -1076,6 +1158,76 @@ int gstvd_op_linear_add_layernorm(gstvd_ctx* c, int M, int K, const float* a, co
   });
 }
 
+static void print_gemm_stamps(const char* tag, const unsigned long long* d_times, int M, int N, int K) {
+  std::vector<unsigned long long> h(256 * 8);
+  cudaMemcpy(h.data(), d_times, h.size() * 8, cudaMemcpyDeviceToHost);
+  unsigned long long t0 = ~0ull; int ctas = 0;
+  for (int i = 0; i < 256; ++i) if (h[i * 8]) { t0 = std::min(t0, h[i * 8]); ++ctas; }
+  double sum[8] = {0}, mx[8] = {0};
+  for (int i = 0; i < 256; ++i) if (h[i * 8]) for (int j = 0; j < 8; ++j) { double v = h[i * 8 + j] ? (double)(h[i * 8 + j] - t0) : 0; sum[j] += v; mx[j] = std::max(mx[j], v); }
+  fprintf(stderr, "[%s M=%d N=%d K=%d ctas=%d] mean/max ns since first CTA start: start %.0f/%.0f prologue %.0f/%.0f pdl_wait %.0f/%.0f first_full|stats %.0f/%.0f last_commit %.0f/%.0f epi_begin %.0f/%.0f epi_end %.0f/%.0f end %.0f/%.0f\n",
+          tag, M, N, K, ctas, sum[0] / ctas, mx[0], sum[1] / ctas, mx[1], sum[2] / ctas, mx[2], sum[3] / ctas, mx[3], sum[4] / ctas, mx[4], sum[5] / ctas, mx[5], sum[6] / ctas, mx[6], sum[7] / ctas, mx[7]);
+}
+
+int gstvd_op_deferred_ln_chain(gstvd_ctx* c, int M, int N, int K1, const float* a1, const float* w1, const float* b1, const float* res0,
+                               const float* gamma1, const float* beta1, const float* w2, const float* b2, const float* gamma2,
+                               const float* beta2, float* out, float* out_x1, void* stream) {
+  if (!c) return GSTVD_ERR_INVALID;
+  return guarded(c, [&] {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c->dtype != kBF16) throw Unsupported("op_deferred_ln_chain: bf16 contexts only");
+    if (M < 1 || M > 512 || N < 64 || N > 32 * kLnStatStride || N % 64 != 0 || K1 < 64 || K1 % 64 != 0) throw InvalidArg("op_deferred_ln_chain: shape");
+    if (!a1 || !w1 || !b1 || !res0 || !gamma1 || !beta1 || !w2 || !b2 || !gamma2 || !beta2 || !out) throw InvalidArg("op_deferred_ln_chain: NULL buffer");
+    Scratch sc;
+    void* a16 = sc.get((size_t)M * K1 * 2); void* w16 = sc.get((size_t)N * K1 * 2); void* r16 = sc.get((size_t)M * N * 2);
+    void* w2f = sc.get((size_t)N * N * 2); float* cd = (float*)sc.get((size_t)2 * N * 4);
+    void* x1 = sc.get((size_t)M * N * 2); void* x2 = sc.get((size_t)M * N * 2); void* y16 = sc.get((size_t)M * N * 2);
+    const int64_t sld = (M + 15) & ~15;
+    float2* st1 = (float2*)sc.get((size_t)sld * kLnStatStride * 8); float2* st2 = (float2*)sc.get((size_t)sld * kLnStatStride * 8);
+    c->launches += launch_cast_f32_to(kBF16, a1, a16, (int64_t)M * K1, s);
+    c->launches += launch_cast_f32_to(kBF16, w1, w16, (int64_t)N * K1, s);
+    c->launches += launch_cast_f32_to(kBF16, res0, r16, (int64_t)M * N, s);
+    c->launches += launch_fold_ln_weights(N, N, w2, gamma1, beta1, b2, w2f, cd, cd + N, s);
+    gemm_tc_init();
+    GemmArgs g1;
+    g1.A = a16; g1.lda = K1; g1.W = w16; g1.ldw = K1; g1.bias = b1; g1.C = x1; g1.ldc = N; g1.M = M; g1.N = N; g1.K = K1;
+    g1.res = r16; g1.ldr = N; g1.stats_out = st1; g1.stats_ld = sld;
+    static const bool want_times = getenv("GSTVD_GEMM_TIMES") != nullptr;   // measurement aid: per-CTA phase timestamps
+    unsigned long long* d_t1 = nullptr; unsigned long long* d_t2 = nullptr;
+    if (want_times) {
+      d_t1 = (unsigned long long*)sc.get(256 * 8 * 8); d_t2 = (unsigned long long*)sc.get(256 * 8 * 8);
+      CUDA_CHECK(cudaMemsetAsync(d_t1, 0, 256 * 8 * 8, s)); CUDA_CHECK(cudaMemsetAsync(d_t2, 0, 256 * 8 * 8, s));
+      g1.dbg_times = d_t1;
+    }
+    c->launches += launch_gemm_tc(g1, c->num_sms, s);
+    GemmArgs g2;
+    g2.A = x1; g2.lda = N; g2.W = w2f; g2.ldw = N; g2.bias = cd + N; g2.C = x2; g2.ldc = N; g2.M = M; g2.N = N; g2.K = N;
+    g2.fold_stats = st1; g2.fold_parts = N / 32; g2.fold_c = cd;
+    g2.res = x1; g2.ldr = N; g2.res_stats = st1; g2.res_parts = N / 32; g2.res_gamma = gamma1; g2.res_beta = beta1;
+    g2.stats_out = st2; g2.stats_ld = sld; g2.dbg_times = d_t2;
+    c->launches += launch_gemm_tc(g2, c->num_sms, s);
+    c->launches += launch_ln_apply_stats(M, N, x2, st2, sld, N / 32, gamma2, beta2, y16, s);
+    c->launches += launch_cast_to_f32(kBF16, y16, out, (int64_t)M * N, s);
+    if (out_x1) c->launches += launch_cast_to_f32(kBF16, x1, out_x1, (int64_t)M * N, s);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    if (want_times) { print_gemm_stamps("ln gemm 1 (res + stats)", d_t1, M, N, K1); print_gemm_stamps("ln gemm 2 (fold + res + stats)", d_t2, M, N, N); }
+  });
+}
+
+int gstvd_debug_self_cache(gstvd_ctx* c, int write, int B, int K, int layer, int kv, float* buf, void* stream) {
+  if (!c || !buf) return GSTVD_ERR_INVALID;
+  return guarded(c, [&] {
+    if (c->dec_layers == 0) throw StateError("debug_self_cache: encoder-only context");
+    if (B < 1 || B > c->B_max || K < 1 || K > c->K_max || layer < 0 || layer >= c->dec_layers || (kv != 0 && kv != 1))
+      throw InvalidArg("debug_self_cache: argument out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n = (int64_t)B * c->T_max * K * c->H;
+    char* base = (char*)c->self_cache.p + ((int64_t)layer * 2 + kv) * n * c->esz;
+    if (write) c->launches += launch_cast_f32_to(c->dtype, buf, base, n, s);
+    else c->launches += launch_cast_to_f32(c->dtype, base, buf, n, s);
+  });
+}
+
 int gstvd_op_attention(gstvd_ctx* c, int dtype, int B, int H, int Lq, int Lk, int D, const float* q, const float* k, const float* v,
                        const float* mask, float neg, int causal, float* out, void* stream) {
   if (!c) return GSTVD_ERR_INVALID;
@@ -1162,7 +1314,7 @@ int gstvd_op_sample(gstvd_ctx* c, int rows, const float* logits, int64_t ldl, co
     }
     c->launches += launch_row_select(rows, c->V, logits, ldl, 1, nullptr, gp->temperature, bt, bc, Lh, kSelMax, (float*)c->sel_val.p,
                                      (int32_t*)c->sel_idx.p, nullptr, s);
-    c->launches += launch_sample_step(rows, T, kSelMax, (const float*)c->sel_val.p, (const int32_t*)c->sel_idx.p, gp->top_k, gp->top_p, gp->seed, nullptr,
+    c->launches += launch_sample_step(rows, T, kSelMax, (const float*)c->sel_val.p, (const int32_t*)c->sel_idx.p, gp->top_k, gp->top_p, gp->seed, (uint64_t)gp->row_offset, nullptr,
                                       (const int*)c->d_step.p, 102, (int32_t*)c->seq.p, (int32_t*)c->cur_tokens.p, (int32_t*)c->prefix.p, T + 1,
                                       out_tokens, s);
   });

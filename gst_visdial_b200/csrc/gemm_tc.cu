@@ -61,8 +61,9 @@ template <int BN, int EW> struct TileCfg {
   static constexpr int kStageWords = 32 * 33;                   // per epilogue warp: 32 rows x 32 words, padded rows
   // wide: 33 KB = 4 x 8 KB (bf16) / 2 x 16 KB (fp32) TMA-store tiles, or 8 generic tiles; skinny: none (direct row stores only)
   static constexpr int kStagingBytes = kSkinny ? 0 : 8 * kStageWords * 4;
-  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kBarBytes + kStagingBytes + 1024;   // +1024: alignment slack
-  static_assert(!kSkinny || 2 * (kSmemBytes + 1024) <= 233472, "skinny configuration must fit two CTAs per SM");
+  static constexpr int kLnVecBytes = EW * 4 * 32 * 4;           // deferred-LayerNorm epilogue: per warp, four 32-float column vectors
+  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kBarBytes + kStagingBytes + 1024;   // +1024: alignment slack; LN kernels add kLnVecBytes
+  static_assert(!kSkinny || 2 * (kSmemBytes + kLnVecBytes + 1024) <= 233472, "skinny configuration must fit two CTAs per SM");
 };
 
 // Epilogue of one W-column block of this warp's 32 accumulator rows: TMEM -> registers (thread = row) -> + bias,
@@ -210,7 +211,114 @@ __device__ __forceinline__ void epilogue_direct_block(const GemmArgs& p, uint32_
   }
 }
 
-template <int BN, int EW>
+// ---- deferred LayerNorm (GemmArgs::fold_stats / res / stats_out; decode step) ------------------------------------------------
+// Row statistics from the per-32-column partials (mean_i, M2_i) a producing GEMM stored, layout [part][row] (ld rows per part) so
+// that the lanes of a warp - consecutive rows - read consecutive addresses.  Equal counts: mean = avg(mean_i),
+// M2 = sum M2_i + 32 sum (mean_i - mean)^2 (Chan et al.); the second sum is taken in one pass over d_i = mean_i - mean_0
+// (sum d^2 - (sum d)^2 / P: the shift keeps the subtraction benign), so no partial has to be kept and every load of the fully
+// unrolled loop is independent - one memory round trip.  Fixed evaluation order -> deterministic.
+// Returns (mean, 1 / sqrt(var + eps)) with the biased variance of models/vilbert_dialog.py:292-296 / nn.LayerNorm(eps=1e-12).
+__device__ __forceinline__ float2 ln_merge_stats(const float2* __restrict__ st, int64_t ld, int parts) {
+  float2 v[kLnStatStride];
+#pragma unroll
+  for (int i = 0; i < kLnStatStride; ++i) v[i] = i < parts ? st[i * ld] : make_float2(0.f, 0.f);
+  const float m0 = v[0].x;
+  float sd = 0.f, sd2 = 0.f, m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnStatStride; ++i) {
+    if (i < parts) {
+      const float d = v[i].x - m0;
+      sd += d; sd2 = fmaf(d, d, sd2); m2 += v[i].y;
+    }
+  }
+  const float inv_p = 1.0f / (float)parts;
+  const float mean = fmaf(sd, inv_p, m0);
+  const float dev = fmaxf(fmaf(-sd * inv_p, sd, sd2), 0.f);
+  const float var = fmaf(32.f, dev, m2) * inv_p * (1.0f / 32.0f);
+  return make_float2(mean, 1.0f / sqrtf(var + kLnEpsDeferred));
+}
+
+// Direct-store epilogue of one 32-column block with the deferred-LayerNorm extras (thread = accumulator row, bf16 output):
+//   v = acc;  fold: v = rstd_a (v - mean_a c_n);  v += bias_n;  residual: v += res (raw: (res - mean_r) rstd_r gamma_n + beta_n);
+//   activation;  round to bf16;  stats_out: (mean, M2) of the 32 ROUNDED values (what the consumers will read back).
+// sv = this warp's shared-memory copy of the block's column vectors: [0] bias / d, [1] c, [2] gamma, [3] beta (32 floats each),
+// fetched before the accumulator is ready so that nothing after the TMEM load waits for global memory.
+__device__ __forceinline__ void epilogue_direct_block_ln(const GemmArgs& p, uint32_t taddr, int row, int col0, float2 fstat, float2 rstat,
+                                                         const uint4* rpre, const float* __restrict__ sv) {
+  uint32_t acc[32];
+  tmem_ld32(taddr, acc);
+  const bool valid = row < p.M && p.dbg != 1;
+  uint4 rres[4];
+  if (p.res != nullptr) {
+    if (rpre != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) rres[c] = rpre[c];
+    } else if (valid) {
+      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res) + (int64_t)row * p.ldr + col0);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) rres[c] = rp[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) rres[c] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  // statistics of the 32 rounded values in one pass, shifted by the first one: d_j = v_j - v_0, mean = v_0 + sum d / 32,
+  // M2 = sum d^2 - (sum d)^2 / 32 (the shift keeps the subtraction benign whatever the common offset of the block)
+  float shift = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int g8 = 0; g8 < 4; ++g8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g8 * 8 + j]);
+    const int cb = col0 + g8 * 8;
+    (void)cb;
+    if (p.fold_stats != nullptr) {
+      const float4 c0 = *reinterpret_cast<const float4*>(sv + 32 + g8 * 8), c1 = *reinterpret_cast<const float4*>(sv + 32 + g8 * 8 + 4);
+      const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fstat.y * fmaf(-fstat.x, cc[j], v[j]);
+    }
+    if (p.bias != nullptr) {
+      const float4 b0 = *reinterpret_cast<const float4*>(sv + g8 * 8), b1 = *reinterpret_cast<const float4*>(sv + g8 * 8 + 4);
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    if (p.res != nullptr) {
+      float r[8];
+      Vec8<bf16>::load(reinterpret_cast<const bf16*>(&rres[g8]), r);
+      if (p.res_stats != nullptr) {
+        const float4 g0 = *reinterpret_cast<const float4*>(sv + 64 + g8 * 8), g1 = *reinterpret_cast<const float4*>(sv + 64 + g8 * 8 + 4);
+        const float4 e0 = *reinterpret_cast<const float4*>(sv + 96 + g8 * 8), e1 = *reinterpret_cast<const float4*>(sv + 96 + g8 * 8 + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = fmaf((r[j] - rstat.x) * rstat.y, gg[j], ee[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    if (p.act == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = gelu_fast(v[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      acc[g8 * 4 + j] = *reinterpret_cast<const uint32_t*>(&h);
+      const float2 back = __bfloat1622float2(h);
+      if (g8 == 0 && j == 0) shift = back.x;
+      const float d0 = back.x - shift, d1 = back.y - shift;
+      s1 += d0 + d1; s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2);
+    }
+  }
+  if (!valid) return;
+  if (p.stats_out != nullptr)
+    p.stats_out[(int64_t)(col0 >> 5) * p.stats_ld + row] = make_float2(fmaf(s1, 1.0f / 32.0f, shift), fmaxf(fmaf(-s1 * (1.0f / 32.0f), s1, s2), 0.f));
+  bf16* dst = reinterpret_cast<bf16*>(p.C) + (int64_t)row * p.ldc + col0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(dst) + 4 * c) = make_uint4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+}
+
+template <int BN, int EW, bool LN = false>
 __global__ void __launch_bounds__((2 + EW) * 32, EW == kEpiWarpsSkinny ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                const __grid_constant__ CUtensorMap tm_c, const GemmArgs p) {
@@ -224,6 +332,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const uint32_t b_base = base + kStages * Cfg::kABytes;
   const uint32_t stage_base = b_base + kStages * Cfg::kBBytes;   // epilogue staging (1024-byte aligned: TMA-store source)
   const uint32_t bar_base = stage_base + Cfg::kStagingBytes;
+  const uint32_t lnvec_base = bar_base + Cfg::kBarBytes;         // deferred-LayerNorm column vectors (per epilogue warp; LN kernels only)
   // barrier layout: full[kStages] | empty[kStages] | tmem_full[2] | tmem_empty[2] | tmem base address (u32)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -318,7 +427,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);         // TMA bytes have landed
           tc_fence_after();
-          if (stamps && iter == 0 && kb == 0) stamps[3] = global_ns();
+          if (stamps && iter == 0 && kb == 0 && !LN) stamps[3] = global_ns();
 #pragma unroll
           for (int ck = 0; ck < kCK; ++ck) {
             const uint64_t a_desc = make_smem_desc(a_base + stage * Cfg::kABytes + ck * Cfg::kAChunk);
@@ -350,6 +459,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
       const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
       const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
+      if constexpr (LN) {
+        // Deferred LayerNorm (a separate instantiation: no register cost elsewhere).  Each warp owns at most one 32-column block
+        // (BN / 32 <= epilogue groups).  Everything that does not need the accumulator is fetched while the main loop runs:
+        //   - the block's column vectors (weights: requested BEFORE the programmatic dependency is awaited) into shared memory,
+        //   - after the wait - row statistics and residual are outputs of preceding kernels, and these warps read them themselves,
+        //     so they wait for the dependency themselves - the merged statistics of this thread's row and its residual values.
+        static_assert(BN / 32 <= kGroups, "one column block per epilogue warp");
+        const int cfirst = n_blk * BN + grp * 32;
+        const bool active = grp < BN / 32 && cfirst < p.N;
+        float* sv = reinterpret_cast<float*>(smem_gen + (lnvec_base - base)) + e * 128;
+        if (active) {
+          sv[lane] = p.bias != nullptr ? __ldg(p.bias + cfirst + lane) : 0.f;
+          sv[32 + lane] = p.fold_c != nullptr ? __ldg(p.fold_c + cfirst + lane) : 0.f;
+          sv[64 + lane] = p.res_gamma != nullptr ? __ldg(p.res_gamma + cfirst + lane) : 0.f;
+          sv[96 + lane] = p.res_beta != nullptr ? __ldg(p.res_beta + cfirst + lane) : 0.f;
+        }
+        if (iter == 0) pdl_wait();
+        const int row = kBM == 128 ? m_blk * BM + quad * 32 + lane : (lane < 16 ? m_blk * kBM + quad * 16 + lane : p.M);
+        const bool rv = active && row < p.M;
+        float2 fstat = make_float2(0.f, 1.f), rstat = make_float2(0.f, 1.f);
+        if (p.fold_stats != nullptr && rv) fstat = ln_merge_stats(p.fold_stats + row, p.stats_ld, p.fold_parts);
+        if (p.res_stats != nullptr && rv) rstat = ln_merge_stats(p.res_stats + row, p.stats_ld, p.res_parts);
+        uint4 rpre[4];
+        const bool have_rpre = p.res != nullptr && active;
+        if (have_rpre) {
+          if (rv) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.res) + (int64_t)row * p.ldr + cfirst);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) rpre[c] = rp[c];
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) rpre[c] = make_uint4(0, 0, 0, 0);
+          }
+        }
+        __syncwarp();                                             // sv complete
+        if (stamps && e == 0 && lane == 0) stamps[3] = global_ns() + (unsigned long long)(__float_as_uint(fstat.x + rstat.x) & 1u);   // statistics merged
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
+        if (stamps && e == 0 && lane == 0) stamps[5] = global_ns();
+        const uint32_t tq = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+        if (active) epilogue_direct_block_ln(p, tq + grp * 32, row, cfirst, fstat, rstat, have_rpre ? rpre : nullptr, sv);
+        tc_fence_before();
+        mbar_arrive(tempty_bar(as));
+        continue;
+      }
       if (p.bias != nullptr && lane == 0) {              // pull this tile's bias segment into L1 while the main loop runs
         const int c0 = n_blk * BN + (e & 7) * (BN / 8);
         if (c0 < p.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + c0));
@@ -545,15 +699,17 @@ const CUtensorMap& get_map_hm(const void* ptr, int D, int L, int G, int64_t LB) 
   return cached_map(key, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int BN, int EW = kEpiWarpsWide>
+template <int BN, int EW = kEpiWarpsWide, bool LN = false>
 void launch_cfg(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
   using Cfg = TileCfg<BN, EW>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EW, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes + (LN ? Cfg::kLnVecBytes : 0));
     if (e != cudaSuccess) throw std::runtime_error(std::string("gemm_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     attr_set = true;
   }
+  const bool ln_args = a_in.fold_stats != nullptr || a_in.res != nullptr || a_in.stats_out != nullptr;
+  if (ln_args != LN) throw std::runtime_error("gemm_tc: deferred-LayerNorm arguments reached a kernel configuration without that epilogue");
   GemmArgs a = a_in;
   const CUtensorMap* ma_ptr = Cfg::kCK > 1 ? &get_map_k3(a.A, a.M, a.K, a.lda, Cfg::kBM, Cfg::kCK) : &get_map(a.A, a.M, a.K, a.lda, Cfg::kBM);
   const CUtensorMap& mb = Cfg::kCK > 1 ? get_map_k3(a.W, a.N, a.K, a.ldw, BN, Cfg::kCK) : get_map(a.W, a.N, a.K, a.ldw, BN);
@@ -586,9 +742,20 @@ void launch_cfg(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
   const int tiles_m = a.hm_tpi > 0 ? a.hm_B * a.hm_tpi : (a.M + Cfg::kBM - 1) / Cfg::kBM;
   const int tiles = tiles_m * ((a.N + BN - 1) / BN);
   if (Cfg::kSkinny && a.tma_store != 2) throw std::runtime_error("gemm_tc: the skinny configuration only has the direct-store epilogue");
+  if (a.fold_stats != nullptr || a.res != nullptr || a.stats_out != nullptr) {
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (a.tma_store != 2 || a.out_f32 || a.N % 32 != 0 || a.ldc % 8 != 0)
+      throw std::runtime_error("gemm_tc: the deferred-LayerNorm epilogue needs the direct-store path, bf16 output and N % 32 == 0");
+    if ((a.bias && !al16(a.bias)) || (a.fold_stats && (!a.fold_c || !al16(a.fold_c) || a.fold_parts < 1 || a.fold_parts > kLnStatStride)) ||
+        ((a.fold_stats || a.res_stats || a.stats_out) && a.stats_ld < a.M) ||
+        (a.res && (!al16(a.res) || a.ldr % 8 != 0)) ||
+        (a.res_stats && (!a.res || !a.res_gamma || !a.res_beta || !al16(a.res_gamma) || !al16(a.res_beta) || a.res_parts != a.N / 32)) ||
+        (a.stats_out && a.N / 32 > kLnStatStride))
+      throw std::runtime_error("gemm_tc: malformed deferred-LayerNorm arguments");
+  }
   const int slots = Cfg::kSkinny ? 2 * num_sms : num_sms;      // resident CTAs: the kernel is persistent over the remaining tiles
   const int grid = tiles < slots ? tiles : slots;
-  launch_k(gemm_tc_kernel<BN, EW>, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmemBytes, stream, *ma_ptr, mb, *mc, a);
+  launch_k(gemm_tc_kernel<BN, EW, LN>, dim3(grid), dim3(Cfg::kThreads), (size_t)(Cfg::kSmemBytes + (LN ? Cfg::kLnVecBytes : 0)), stream, *ma_ptr, mb, *mc, a);
 }
 
 }  // namespace
@@ -624,6 +791,14 @@ int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream, bool 
   if (a.K % 8 != 0) throw std::runtime_error("gemm_tc: K must be a multiple of 8");
   if (a.hm_D > 0 && (a.hm_D % 32 != 0)) throw std::runtime_error("gemm_tc: head-major scatter needs head_dim % 32 == 0");
   gemm_tc_init();
+  if (a.fold_stats != nullptr || a.res != nullptr || a.stats_out != nullptr) {
+    // deferred-LayerNorm epilogue (decode step): the M = 64 two-per-SM configuration with 32-column tiles while they fit the
+    // resident slots (the N = H projections, the only ones that write statistics), 64-column tiles of 128 rows for the wide ones
+    if (a.K % BK != 0 || a.M > 4 * BM) throw std::runtime_error("gemm_tc: the deferred-LayerNorm epilogue needs K % 64 == 0 and M <= 512");
+    if (((a.M + 63) / 64) * ((a.N + 31) / 32) <= 2 * num_sms) launch_cfg<32, kEpiWarpsSkinny, true>(a, num_sms, stream);
+    else { if (a.stats_out != nullptr) throw std::runtime_error("gemm_tc: statistics are only written by 32-column tiles"); launch_cfg<64, kEpiWarpsWide, true>(a, num_sms, stream); }
+    return 1;
+  }
   if (launch_gemm_splitk_if_selected(a, stream)) return 1;         // EXPERIMENTAL cluster split-K kernel for decode problems (env GSTVD_GEMM_SPLITK)
   if (launch_gemm_tc2_if_selected(a, num_sms, stream)) return 1;   // EXPERIMENTAL CTA-pair kernel (env GSTVD_GEMM_2CTA)
   const int tiles_m = (a.M + BM - 1) / BM;

@@ -48,9 +48,27 @@ struct GemmArgs {
   int hm_D = 0, hm_L = 0, hm_G = 0, hm_B = 0;
   int hm_tpi = 0;      // set by launch_gemm_tc: head-major TMA mode, M tiles per image (tiles never straddle images)
   int tma_store = 0;   // set by launch_gemm_tc: 1 = epilogue stores through a TMA tensor map, 2 = direct 16-byte row stores (skinny problems)
+  // ---- deferred LayerNorm (decode step, direct-store epilogue only) ----
+  // The decoder's dense -> LayerNorm(x + input) pairs (HF BertSelfOutput / BertOutput, call site models/visual_dialog_decoder.py:300-311)
+  // run without a LayerNorm kernel: the producing GEMM stores the RAW sum x = A W^T + b + residual (bf16) and, per 32-column block,
+  // the row's (mean, M2) of the stored values; every consumer of LN(x) applies it on the fly from the merged statistics:
+  //   as the next GEMM's A operand:  LN(x) W^T + b = rstd (x W'^T - mean c) + d   with W' = W * gamma (columns), c_n = sum_k W'_nk,
+  //                                  d_n = sum_k beta_k W_nk + b_n  (W', c, d are prepared once by launch_fold_ln_weights);
+  //   as the next residual:          (x - mean) rstd gamma + beta, evaluated in the epilogue.
+  int64_t stats_ld = 0;                 // row capacity of every statistics buffer below: layout [part][stats_ld rows]
+  const float2* fold_stats = nullptr;   // partial (mean, M2) of the raw A rows; non-null: W is W', bias is d
+  int fold_parts = 0;                   // partials per row (= raw width / 32)
+  const float* fold_c = nullptr;        // [N]
+  const void* res = nullptr; int64_t ldr = 0;       // bf16 residual added before the activation / rounding (null: none)
+  const float2* res_stats = nullptr; int res_parts = 0;   // non-null: `res` is raw, the residual is its LayerNorm
+  const float* res_gamma = nullptr; const float* res_beta = nullptr;
+  float2* stats_out = nullptr;          // (mean, M2) of this launch's stored values per 32-column block
   unsigned long long* dbg_times = nullptr;   // measurement aid: per-CTA globaltimer stamps (8 per CTA)
   int dbg = 0;   // measurement aid (env GSTVD_GEMM_DBG): 1 = epilogue without global stores, 2 = epilogue skipped, 3 = no MMA
 };
+
+constexpr int kLnStatStride = 32;   // partial statistics per row (rows of at most 1024 columns)
+constexpr float kLnEpsDeferred = 1e-12f;
 
 // SIMT GEMM: dtype kF32 (all fp32) or kBF16 (bf16 operands, fp32 accumulate; debugging aid)
 int launch_gemm_simt(const GemmArgs& a, int dtype, cudaStream_t stream);
@@ -87,6 +105,12 @@ bool attention_mma_supported(const AttnArgs& a);
 // y = LN(x + residual) ; rows x width ; dtype of x/residual/y = dtype ; gamma/beta fp32
 int launch_add_layernorm(int dtype, int rows, int width, const void* x, int64_t ldx, const void* residual, int64_t ldr,
                          const float* gamma, const float* beta, void* y, int64_t ldy, cudaStream_t stream);
+// deferred LayerNorm (see GemmArgs): folded weight preparation (fp32 W [N,K] -> bf16 W' + c[N] + d[N]) and the materialising
+// normalisation of a raw bf16 tensor from its stored partial statistics (width = 32 * parts)
+int launch_fold_ln_weights(int N, int K, const float* W, const float* gamma, const float* beta, const float* bias, void* Wf, float* c,
+                           float* d, cudaStream_t stream);
+int launch_ln_apply_stats(int rows, int width, const void* x, const float2* stats, int64_t stats_ld, int parts, const float* gamma,
+                          const float* beta, void* y, cudaStream_t stream);
 // text embeddings: y[row] = LN(word[id] + pos[p] + type[seg]);  positions = row % L + pos_offset(*d_pos_offset if non-null)
 int launch_embed_text(int dtype, int rows, int L, int width, const int64_t* ids, const int64_t* seg, const int* d_pos_offset,
                       int eos_to_pad, const float* word, const float* pos, const float* type, const float* type_ext,
@@ -117,7 +141,8 @@ struct DecodeGeom {
 };
 // self-attention for one new position per row: appends k/v at position *d_step and attends over 0..*d_step
 // qkv [M, 3H]; cache layout [layer][kv][b][t][k][H]
-int launch_dec_self_attn(int dtype, const DecodeGeom& g, int layer, const void* qkv, void* self_cache, const int* d_step,
+// step_host >= 0: the caller knows the step index (must equal *d_step); the lean kernel then only loads positions <= step
+int launch_dec_self_attn(int dtype, const DecodeGeom& g, int layer, const void* qkv, void* self_cache, const int* d_step, int step_host,
                          const uint8_t* anc, void* out, cudaStream_t stream);
 // the lean bf16 / 64-dim kernel will run for these arguments (default on; env GSTVD_SELF_V2=0 disables it)
 bool dec_self_attn_v2_active(int dtype, const DecodeGeom& g, const void* qkv, const void* self_cache, const void* out);
@@ -175,14 +200,14 @@ int launch_ngram_ban(int rows, int Lh, const int64_t* hist_ids, const int64_t* h
                      cudaStream_t stream);
 // sample-mode selection from row_select output; writes seq[row, step] and cur_tokens[row], prefix[row, step+1]
 int launch_sample_step(int rows, int T, int nsel, const float* sel_val, const int32_t* sel_idx, int top_k, float top_p,
-                       uint64_t seed, const uint64_t* d_seed, const int* d_step, int eos, int32_t* seq, int32_t* cur_tokens, int32_t* prefix,
+                       uint64_t seed, uint64_t row_offset, const uint64_t* d_seed, const int* d_step, int eos, int32_t* seq, int32_t* cur_tokens, int32_t* prefix,
                        int prefix_stride, int32_t* out_tokens, cudaStream_t stream);
 int launch_sample_init(int rows, int T, int start_token, int32_t* seq, int32_t* cur_tokens, int32_t* prefix,
                        int prefix_stride, int* d_step, cudaStream_t stream);
 int launch_sample_finalize(int rows, int T, int eos, const int32_t* seq, int64_t* out_ids, cudaStream_t stream);
 int launch_step_advance(int* d_step, cudaStream_t stream);
 // device-side scalar set (a pageable-memory cudaMemcpyAsync would synchronise the stream with the host)
-int launch_set_u64(uint64_t* dst, uint64_t v, cudaStream_t stream);
+int launch_set_u64(uint64_t* dst, uint64_t v, uint64_t v1, cudaStream_t stream);   // dst[0] = v, dst[1] = v1
 
 // teacher-forced scoring helpers
 int launch_shift_labels(int B, int L, int64_t* dec_ids, int64_t* labels, int eos, cudaStream_t stream);

@@ -230,6 +230,67 @@ image_embed_ln_kernel(int rows, int width, const T* __restrict__ x, const float*
   ln_finish<T>(v, width, lane, gamma, beta, y + (int64_t)row * width);
 }
 
+// ---- deferred LayerNorm (decode step, GemmArgs::fold_stats / res_stats / stats_out) ---------------------------------------------
+// Weight preparation, once per weight load: W'[n][k] = bf16(W[n][k] gamma[k]); c[n] = sum_k W'[n][k] (of the ROUNDED values: it
+// cancels the mean term of what the tensor core actually multiplies); d[n] = sum_k beta[k] W[n][k] + bias[n].  One warp per row n.
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+fold_ln_weights_kernel(int N, int K, const float* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       const float* __restrict__ bias, bf16* __restrict__ Wf, float* __restrict__ c, float* __restrict__ d) {
+  const int n = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float cs = 0.f, ds = 0.f;
+  for (int k = lane * 8; k < K; k += 256) {
+    float w[8], g[8], b[8], o[8];
+    Vec8<float>::load(W + (int64_t)n * K + k, w);
+    Vec8<float>::load(gamma + k, g);
+    Vec8<float>::load(beta + k, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j] = to_f32(__float2bfloat16_rn(w[j] * g[j]));
+      cs += o[j];
+      ds = fmaf(b[j], w[j], ds);
+    }
+    Vec8<bf16>::store(Wf + (int64_t)n * K + k, o);
+  }
+  cs = warp_sum(cs); ds = warp_sum(ds);
+  if (lane == 0) { c[n] = cs; d[n] = ds + (bias ? bias[n] : 0.f); }
+}
+
+// y = LN(x) for a raw bf16 row whose statistics were stored by the producing GEMM as per-32-column partials (mean_i, M2_i):
+// the one place of a decode step where the normalised tensor is materialised (input of the LM head).  One warp per row.
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+ln_apply_stats_kernel(int rows, int width, const bf16* __restrict__ x, const float2* __restrict__ stats, int64_t stats_ld, int parts,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, bf16* __restrict__ y) {
+  const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  float g[kMaxChunks][8], b[kMaxChunks][8];
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int col = (lane + 32 * c) * 8;
+    if (col < width) { Vec8<float>::load(gamma + col, g[c]); Vec8<float>::load(beta + col, b[c]); }
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+  if (row >= rows) return;
+  const float2 mine = lane < parts ? stats[(int64_t)lane * stats_ld + row] : make_float2(0.f, 0.f);
+  const float mean = warp_sum(mine.x) / (float)parts;            // butterfly order: identical in every lane, deterministic
+  const float dv = lane < parts ? mine.x - mean : 0.f;
+  const float var = warp_sum(fmaf(32.f * dv, dv, mine.y)) / (32.f * (float)parts);
+  const float rstd = 1.0f / sqrtf(var + kLnEpsDeferred);
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int col = (lane + 32 * c) * 8;
+    if (col < width) {
+      float v[8], o[8];
+      Vec8<bf16>::load(x + (int64_t)row * width + col, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf((v[j] - mean) * rstd, g[c][j], b[c][j]);
+      Vec8<bf16>::store(y + (int64_t)row * width + col, o);
+    }
+  }
+}
+
 template <typename T>
 __global__ void cast_from_f32_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n) {
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
@@ -319,6 +380,22 @@ int launch_add_layernorm(int dtype, int rows, int width, const void* x, int64_t 
     launch_k(add_layernorm_kernel<float>, grid_rows(rows), kRowsPerBlock * 32, 0, stream, rows, width, (const float*)x, ldx, (const float*)residual, ldr, gamma, beta, (float*)y, ldy);
   else
     launch_k(add_layernorm_kernel<bf16>, grid_rows(rows), kRowsPerBlock * 32, 0, stream, rows, width, (const bf16*)x, ldx, (const bf16*)residual, ldr, gamma, beta, (bf16*)y, ldy);
+  return 1;
+}
+
+int launch_fold_ln_weights(int N, int K, const float* W, const float* gamma, const float* beta, const float* bias, void* Wf, float* c,
+                           float* d, cudaStream_t stream) {
+  if (K % 8 != 0) throw std::runtime_error("fold_ln_weights: K % 8 != 0");
+  fold_ln_weights_kernel<<<grid_rows(N), kRowsPerBlock * 32, 0, stream>>>(N, K, W, gamma, beta, bias, (bf16*)Wf, c, d);
+  return 1;
+}
+
+int launch_ln_apply_stats(int rows, int width, const void* x, const float2* stats, int64_t stats_ld, int parts, const float* gamma,
+                          const float* beta, void* y, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  check_width(width);
+  if (parts < 1 || parts > 32 || parts * 32 != width) throw std::runtime_error("ln_apply_stats: width must be 32 * parts <= 1024");
+  launch_k(ln_apply_stats_kernel, grid_rows(rows), kRowsPerBlock * 32, 0, stream, rows, width, (const bf16*)x, stats, stats_ld, parts, gamma, beta, (bf16*)y);
   return 1;
 }
 

@@ -589,7 +589,7 @@ __global__ void sample_init_kernel(int rows, int T, int start_token, int32_t* se
 }
 
 __global__ void sample_step_kernel(int rows, int T, int nsel, const float* __restrict__ sel_val, const int32_t* __restrict__ sel_idx,
-                                   int top_k, float top_p, uint64_t seed, const uint64_t* __restrict__ d_seed,
+                                   int top_k, float top_p, uint64_t seed, uint64_t row_offset, const uint64_t* __restrict__ d_seed,
                                    const int* __restrict__ d_step, int eos, int32_t* seq, int32_t* cur_tokens, int32_t* prefix, int prefix_stride, int32_t* out_tokens) {
   pdl_wait();
   pdl_launch_dependents();
@@ -619,8 +619,10 @@ __global__ void sample_step_kernel(int rows, int T, int nsel, const float* __res
   }
   int choice = 0;
   if (kept > 1 && top_k > 1) {     // top_k == 1 is the deterministic greedy path (lowest index among exact ties)
-    const uint64_t sd = d_seed ? *d_seed : seed;
-    const uint64_t h = splitmix64(sd ^ splitmix64(((uint64_t)row << 20) ^ (uint64_t)step));
+    // keyed by the GLOBAL row (d_seed[1] = row offset of this batch): the draws of an image are the same whichever batch / rank holds it
+    const uint64_t sd = d_seed ? d_seed[0] : seed;
+    const uint64_t grow = (uint64_t)row + (d_seed ? d_seed[1] : row_offset);
+    const uint64_t h = splitmix64(sd ^ splitmix64((grow << 20) ^ (uint64_t)step));
     const float u = (float)(h >> 40) * (1.0f / 16777216.0f) * sum;
     float c = 0.f;
     choice = kept - 1;
@@ -644,7 +646,7 @@ __global__ void sample_finalize_kernel(int rows, int T, int eos, const int32_t* 
   }
 }
 
-__global__ void set_u64_kernel(uint64_t* dst, uint64_t v) { if (threadIdx.x == 0 && blockIdx.x == 0) *dst = v; }
+__global__ void set_u64_kernel(uint64_t* dst, uint64_t v, uint64_t v1) { if (threadIdx.x == 0 && blockIdx.x == 0) { dst[0] = v; dst[1] = v1; } }
 
 __global__ void step_advance_kernel(int* d_step) {
   pdl_wait();
@@ -764,10 +766,10 @@ int launch_ngram_ban(int rows, int Lh, const int64_t* hist_ids, const int64_t* h
   return 1;
 }
 int launch_sample_step(int rows, int T, int nsel, const float* sel_val, const int32_t* sel_idx, int top_k, float top_p,
-                       uint64_t seed, const uint64_t* d_seed, const int* d_step, int eos, int32_t* seq, int32_t* cur_tokens, int32_t* prefix,
+                       uint64_t seed, uint64_t row_offset, const uint64_t* d_seed, const int* d_step, int eos, int32_t* seq, int32_t* cur_tokens, int32_t* prefix,
                        int prefix_stride, int32_t* out_tokens, cudaStream_t stream) {
   if (top_k < 1 || top_k > nsel) throw std::runtime_error("sample_step: top_k out of range");
-  launch_k(sample_step_kernel, dim3((rows + 63) / 64), dim3(64), 0, stream, rows, T, nsel, sel_val, sel_idx, top_k, top_p, seed, d_seed, d_step, eos, seq,
+  launch_k(sample_step_kernel, dim3((rows + 63) / 64), dim3(64), 0, stream, rows, T, nsel, sel_val, sel_idx, top_k, top_p, seed, row_offset, d_seed, d_step, eos, seq,
                                                           cur_tokens, prefix, prefix_stride, out_tokens);
   return 1;
 }
@@ -780,8 +782,8 @@ int launch_sample_finalize(int rows, int T, int eos, const int32_t* seq, int64_t
   sample_finalize_kernel<<<(rows + 63) / 64, 64, 0, stream>>>(rows, T, eos, seq, out_ids);
   return 1;
 }
-int launch_set_u64(uint64_t* dst, uint64_t v, cudaStream_t stream) {
-  set_u64_kernel<<<1, 32, 0, stream>>>(dst, v);
+int launch_set_u64(uint64_t* dst, uint64_t v, uint64_t v1, cudaStream_t stream) {
+  set_u64_kernel<<<1, 32, 0, stream>>>(dst, v, v1);
   return 1;
 }
 int launch_step_advance(int* d_step, cudaStream_t stream) {

@@ -39,7 +39,7 @@ def _model_call(model, st, dec_input_ids, **kw):
 
 
 def generate_dialogs(a_model, batch, q_model=None, questions=None, num_rounds=10, a_kwargs=None, q_kwargs=None,
-                     with_ppl=True, device=None, trim_history=True, max_new_tokens=18) -> DialogResult:
+                     with_ppl=True, device=None, trim_history=True, max_new_tokens=18, seed=None, row_offset=0) -> DialogResult:
     """``batch`` uses the reference dataloader's keys (generate.py:95-111).  Either ``q_model`` or ``questions``
     (int64 [B, num_rounds, 18], zero padded, each ending in [SEP]) must be given.  ``a_kwargs`` / ``q_kwargs`` are the
     decoding kwargs of EncoderDecoderModel.forward; defaults are generate.py:138-141 / :177-180.
@@ -83,11 +83,16 @@ def generate_dialogs(a_model, batch, q_model=None, questions=None, num_rounds=10
     def bound():
         return int(ub.max().clamp(max=Lmax)) if ub is not None else None
 
+    from .models.visual_dialog_model import derive_seed
+    base_seed = am.params.get("seed", 0) if seed is None else seed
+    a_user, q_user = a_kwargs, q_kwargs
     for rnd in range(num_rounds):
+        a_kwargs = a_user if "seed" in a_user else dict(a_user, seed=derive_seed(base_seed, "a", rnd), row_offset=row_offset)
         if q_model is None:
             ques = questions[:, rnd].contiguous()
         else:
-            ques = _model_call(q_model, st, dec_start, enc_valid_len=bound(), **q_kwargs)
+            qk = q_user if "seed" in q_user else dict(q_user, seed=derive_seed(base_seed, "q", rnd), row_offset=row_offset)
+            ques = _model_call(q_model, st, dec_start, enc_valid_len=bound(), **qk)
         eng.splice(st["ids"], st["seg"], st["mask"], enc_len, ques, segment_value=-1, strip_sep=False, abnormal=abnormal)
         if ub is not None:
             ub = ub + (q_host[:, rnd] if q_host is not None else max_new_tokens)

@@ -154,13 +154,16 @@ class Engine:
         check(self.ctx, self.lib.gstvd_prefill_cross(self.ctx, B, Le, _ptr(h), _ptr(m), self._stream()))
 
     def generate(self, B, num_beams=1, temperature=1.0, top_k=1, top_p=0.0, ngram_blocking_size=0, seed=0,
-                 max_new_tokens=None, hist_ids=None, hist_segments=None, want_scores=False):
+                 max_new_tokens=None, hist_ids=None, hist_segments=None, want_scores=False, row_offset=0):
+        """``row_offset``: global index of row 0; the sampler is keyed by (seed, row_offset + row, step), so an image draws the
+        same tokens whichever batch or rank it lands in."""
         gp = GstvdGenParams()
         gp.mode = GSTVD_SELECT_BEAM if num_beams > 1 else GSTVD_SELECT_SAMPLE
         gp.num_beams = int(num_beams)
         gp.max_new_tokens = int(max_new_tokens or self.max_new_tokens)
         gp.top_k, gp.temperature, gp.top_p = int(top_k), float(temperature), float(top_p)
         gp.ngram_blocking_size, gp.seed = int(ngram_blocking_size), int(seed) & (2**64 - 1)
+        gp.row_offset = int(row_offset)
         hid = self._dev(hist_ids, torch.int64) if ngram_blocking_size > 0 else None
         hseg = self._dev(hist_segments, torch.int64) if ngram_blocking_size > 0 else None
         Lh = hid.shape[1] if hid is not None else 0
@@ -234,6 +237,35 @@ class Engine:
                                                                int(cluster), _ptr(y), self._stream()))
         return y
 
+    def op_deferred_ln_chain(self, a1, w1, b1, res0, gamma1, beta1, w2, b2, gamma2, beta2, want_x1=False):
+        """LN2(LN1(x1) w2^T + b2 + LN1(x1)) with x1 = a1 w1^T + b1 + res0, through the decode step's deferred-LayerNorm GEMM
+        epilogues (no LayerNorm kernel between the two GEMMs).  bf16 contexts; fp32 tensors in and out."""
+        f = lambda t: self._dev(t, torch.float32)
+        a1, w1, b1, res0, gamma1, beta1, w2, b2, gamma2, beta2 = map(f, (a1, w1, b1, res0, gamma1, beta1, w2, b2, gamma2, beta2))
+        M, K1 = a1.shape
+        N = w1.shape[0]
+        assert w1.shape == (N, K1) and w2.shape == (N, N) and res0.shape == (M, N)
+        out = torch.empty(M, N, dtype=torch.float32, device=self.device)
+        x1 = torch.empty(M, N, dtype=torch.float32, device=self.device) if want_x1 else None
+        check(self.ctx, self.lib.gstvd_op_deferred_ln_chain(self.ctx, M, N, K1, _ptr(a1), _ptr(w1), _ptr(b1), _ptr(res0), _ptr(gamma1),
+                                                            _ptr(beta1), _ptr(w2), _ptr(b2), _ptr(gamma2), _ptr(beta2), _ptr(out), _ptr(x1),
+                                                            self._stream()))
+        return (out, x1) if want_x1 else out
+
+    def debug_self_cache(self, B, K, layer, kv, values=None):
+        """Test access to the self-attention KV cache of one (layer, kv) in the (B, K) layout: fp32 [B, max_new_tokens, K, hidden].
+        ``values`` given: written into the cache; else the current content is returned."""
+        H = self.cfg.hidden_size
+        if values is not None:
+            buf = self._dev(values, torch.float32)
+            assert buf.shape == (B, self.max_new_tokens, K, H)
+            check(self.ctx, self.lib.gstvd_debug_self_cache(self.ctx, 1, B, K, layer, kv, _ptr(buf), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()
+            return None
+        buf = torch.empty(B, self.max_new_tokens, K, H, dtype=torch.float32, device=self.device)
+        check(self.ctx, self.lib.gstvd_debug_self_cache(self.ctx, 0, B, K, layer, kv, _ptr(buf), self._stream()))
+        return buf
+
     def op_attention(self, q, k, v, heads, mask=None, neg=-10000.0, causal=False, dtype=None):
         q, k, v = self._dev(q, torch.float32), self._dev(k, torch.float32), self._dev(v, torch.float32)
         m = self._dev(mask, torch.float32)
@@ -266,12 +298,12 @@ class Engine:
         return out, sc
 
     def op_sample(self, logits, step, temperature=1.0, top_k=1, top_p=0.0, ngram_blocking_size=0, seed=0, hist_ids=None,
-                  hist_segments=None, prefix=None):
+                  hist_segments=None, prefix=None, row_offset=0):
         lg = self._dev(logits, torch.float32)
         gp = GstvdGenParams()
         gp.mode, gp.num_beams, gp.max_new_tokens = GSTVD_SELECT_SAMPLE, 1, self.max_new_tokens
         gp.top_k, gp.temperature, gp.top_p = int(top_k), float(temperature), float(top_p)
-        gp.ngram_blocking_size, gp.seed = int(ngram_blocking_size), int(seed)
+        gp.ngram_blocking_size, gp.seed, gp.row_offset = int(ngram_blocking_size), int(seed) & (2**64 - 1), int(row_offset)
         hid, hseg, pre = self._dev(hist_ids, torch.int64), self._dev(hist_segments, torch.int64), self._dev(prefix, torch.int64)
         rows = lg.shape[0]
         out = torch.empty(rows, device=self.device, dtype=torch.int32)

@@ -75,15 +75,30 @@ class JsonlWriter:
         self._t = threading.Thread(target=run, daemon=True)
         self._t.start()
 
+    def _put(self, item) -> None:
+        """Bounded put that cannot deadlock on a dead writer thread (full disk, ...): the error / liveness check is repeated
+        while the queue is full instead of only once before a blocking put."""
+        while True:
+            if self._err is not None:
+                raise self._err
+            if not self._t.is_alive():
+                raise RuntimeError(f"JsonlWriter: writer thread for {self.path} is gone")
+            try:
+                self._q.put(item, timeout=0.5)
+                return
+            except queue.Full:
+                continue
+
     def write(self, records: list) -> None:
-        if self._err is not None:
-            raise self._err
-        self._q.put(list(records))
+        self._put(list(records))
 
     def close(self) -> int:
-        self._q.put(None)
-        self._t.join()
-        self._f.close()
+        try:
+            if self._t.is_alive() and self._err is None:
+                self._put(None)
+            self._t.join()
+        finally:
+            self._f.close()
         if self._err is not None:
             raise self._err
         return self.count

@@ -10,6 +10,21 @@ from .visual_dialog_decoder import Seq2SeqLMOutput
 from .visual_dialog_encoder import _EngineOwner
 
 
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return x ^ (x >> 31)
+
+
+def derive_seed(base, role, index) -> int:
+    """64-bit sampling seed from the run seed, the model role ('enc_dec_q' / 'enc_dec_a' ...) and a counter (call or round)."""
+    tag = 0xCBF29CE484222325
+    for ch in str(role).encode():                      # FNV-1a over the whole role string
+        tag = ((tag ^ ch) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return _splitmix64(_splitmix64(int(base) & 0xFFFFFFFFFFFFFFFF) ^ _splitmix64(tag) ^ ((int(index) + 1) * 0x632BE59BD9B4E019 & 0xFFFFFFFFFFFFFFFF))
+
+
 class VLFusion(nn.Module):
     """Parameters of models/visual_dialog_model.py:123-129; the projection itself runs inside the engine."""
 
@@ -44,6 +59,7 @@ class EncoderDecoderModel(_EngineOwner, nn.Module):
         self.config = {"encoder": encoder.config.to_dict(), "decoder": decoder.config.to_dict()}
         self._init_engine_state(params)
         self._calls = 0
+        self._start_checked = False
         encoder._version = self._version      # one change counter for the whole model
         # plain attributes, not sub-modules: a registered back-reference would make the module tree cyclic
         object.__setattr__(encoder, "_owner", self)
@@ -56,16 +72,18 @@ class EncoderDecoderModel(_EngineOwner, nn.Module):
     def _score(self, eng, dec_input_ids, dec_attention_mask, dec_labels, loss_reduction, want_logits=True):
         if not dec_input_ids.is_contiguous() or dec_input_ids.dtype != torch.int64:
             raise ValueError("dec_input_ids must be a contiguous int64 tensor (it is modified in place like the reference does)")
-        loss, logits = eng.score(dec_input_ids, dec_attention_mask, dec_labels, want_logits=want_logits)
         mode = self.params['mode']
+        want_mean = ('train' in mode or 'eval' in mode) and loss_reduction
+        # CrossEntropyLoss(ignore_index=0, reduction='mean') divides by the number of non-ignored targets and returns NaN when there
+        # are none (models/visual_dialog_decoder.py:70-77).  The labels are the ids shifted left (:54-56), counted here BEFORE the
+        # call replaces [SEP] by [PAD] in dec_input_ids in place.
+        n = None
+        if want_mean:
+            n = (dec_input_ids[:, 1:] != 0).sum() if dec_labels is None else (dec_labels != 0).sum()
+        loss, logits = eng.score(dec_input_ids, dec_attention_mask, dec_labels, want_logits=want_logits)
         if 'train' in mode or 'eval' in mode:
             if loss_reduction:
-                # CrossEntropyLoss(ignore_index=0): mean over the non-ignored targets
-                if dec_labels is None:
-                    n = (loss != 0).sum().clamp(min=1)   # ignored positions carry an exact 0
-                else:
-                    n = (dec_labels != 0).sum().clamp(min=1)
-                loss = loss.sum() / n
+                loss = loss.sum() / n                    # 0 / 0 = NaN like the reference when every target is ignored
             else:
                 loss = loss.reshape(-1)
         else:
@@ -110,8 +128,15 @@ class EncoderDecoderModel(_EngineOwner, nn.Module):
             return out.loss, out.logits
 
         # decode mode (models/visual_dialog_model.py:74-120): 18 new tokens, PAD after the first [SEP]
+        self._check_decoder_start(dec_input_ids)
         self._calls += 1
         seed = decoding_kwargs.get("seed")
+        if seed is None:
+            # The reference draws independent torch.multinomial samples per call.  The device sampler is counter based, keyed by
+            # (seed, global row, step): derive the seed from the run seed (options.py:43 -seed), the model's role (questioner and
+            # teacher must not replay the same uniforms) and this model's call counter.  Callers that want draws that do not
+            # depend on the batch / rank split pass seed= and row_offset= themselves (gst_visdial_b200/dialog.py does).
+            seed = derive_seed(self.params.get("seed", 0), self.params.get("model", ""), self._calls)
         return eng.generate(
             B,
             num_beams=int(decoding_kwargs.get("num_beams", 1)),
@@ -119,7 +144,23 @@ class EncoderDecoderModel(_EngineOwner, nn.Module):
             top_k=decoding_kwargs['top_k'],
             top_p=decoding_kwargs['top_p'],
             ngram_blocking_size=decoding_kwargs['ngram_blocking_size'],
-            seed=self._calls if seed is None else seed,
+            seed=seed,
+            row_offset=int(decoding_kwargs.get("row_offset", 0)),
             hist_ids=enc_input_ids,
             hist_segments=enc_segments,
         )
+
+    def _check_decoder_start(self, dec_input_ids):
+        """The reference continues from whatever prefix the caller passes (models/visual_dialog_model.py:86-110); every caller on
+        the path passes a single [CLS] (generate.py:111, dataloader_cc12m_gen.py:99).  The engine's cached decode starts from
+        bos_token_id, so anything else is refused instead of silently ignored."""
+        if dec_input_ids is None:
+            return
+        bos = int(getattr(self.decoder.config, "bos_token_id", 101) or 101)
+        if dec_input_ids.dim() != 2 or dec_input_ids.shape[1] != 1:
+            raise ValueError(f"decode mode starts from one start token per row (dec_input_ids [B, 1]), got {tuple(dec_input_ids.shape)}")
+        if not self._start_checked:
+            # one host read per model instance (a device sync): later calls of the round loop pass the same tensor
+            if not bool((dec_input_ids == bos).all()):
+                raise ValueError(f"decode mode starts from bos_token_id = {bos}; other prefixes are not supported")
+            self._start_checked = True

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GSTVD_ABI_VERSION 1
+#define GSTVD_ABI_VERSION 2
 #define GSTVD_MAX_CONNECTIONS 16
 
 typedef enum {
@@ -89,7 +89,9 @@ typedef struct {
   float temperature;          /* sample mode: logits / temperature */
   float top_p;                /* sample mode: nucleus threshold applied inside the top-k set; 0 = off */
   int32_t ngram_blocking_size;/* 0 = off; n: ban tokens completing an n-gram of the question history */
-  uint64_t seed;              /* sample mode RNG seed (counter-based; reproducible per (seed,row,step)) */
+  uint64_t seed;              /* sample mode RNG seed (counter-based; reproducible per (seed, row_offset + row, step)) */
+  int64_t row_offset;         /* global index of row 0 (e.g. the image index of the first sample of this batch / shard): the
+                                 draws of an image do not depend on how the images were split into batches or ranks */
 } gstvd_gen_params;
 
 #define GSTVD_MAX_TOP_K 16
@@ -208,6 +210,22 @@ int gstvd_op_beam_end(gstvd_ctx* ctx, int64_t* out_ids, float* out_scores, void*
 int gstvd_op_sample(gstvd_ctx* ctx, int rows, const float* logits, int64_t ldl, const gstvd_gen_params* params,
                     const int64_t* hist_ids, const int64_t* hist_segments, int Lh, const int64_t* prefix, int prefix_len,
                     int step, int32_t* out_tokens, void* stream);
+
+/* The deferred-LayerNorm chain of a decode step on caller-supplied operands (bf16 contexts; all buffers fp32 on the device,
+ * rounded to bf16 inside): the dense -> LayerNorm(x + input) pairs of HF BertSelfOutput / BertOutput (call site
+ * models/visual_dialog_decoder.py:300-311) without a LayerNorm kernel in between -
+ *   x1 = a1 w1^T + b1 + res0            stored raw (bf16) with per-32-column row statistics
+ *   x2 = LN1(x1) w2^T + b2 + LN1(x1)    LN1 applied inside the second GEMM (folded weights for the operand, on the fly for the residual)
+ *   out = LN2(x2)                       materialised from the stored statistics
+ * a1 [M,K1], w1 [N,K1], res0 [M,N], w2 [N,N]; N % 64 == 0, N <= 1024, K1 % 64 == 0, M <= 512.  out_x1 (raw x1, may be NULL). */
+int gstvd_op_deferred_ln_chain(gstvd_ctx* ctx, int M, int N, int K1, const float* a1, const float* w1, const float* b1,
+                               const float* res0, const float* gamma1, const float* beta1, const float* w2, const float* b2,
+                               const float* gamma2, const float* beta2, float* out, float* out_x1, void* stream);
+
+/* Test access to the self-attention KV cache in the layout a generate call with (B, K) uses: buf fp32 [B, max_new_tokens, K,
+ * hidden] on the device for one (layer, kv in {0: key, 1: value}); write != 0 stores buf into the cache (rounded to the
+ * compute dtype), else reads it back.  Lets the tests check gstvd_reorder_cache against index_select(0, beam_idx) directly. */
+int gstvd_debug_self_cache(gstvd_ctx* ctx, int write, int B, int K, int layer, int kv, float* buf, void* stream);
 
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t gstvd_launch_count(const gstvd_ctx* ctx);

@@ -39,3 +39,18 @@ def rel_rms(a: torch.Tensor, ref: torch.Tensor) -> float:
 
 def max_abs(a: torch.Tensor, ref: torch.Tensor) -> float:
     return float((a.double() - ref.double()).abs().max())
+
+
+def bf16_report(a: torch.Tensor, ref: torch.Tensor, rtol: float = 2e-2) -> dict:
+    """The three readings of "2e-2 relative"  for rows [n, width]: rel-rms over everything; the worst
+    max|delta| / rms(reference row); and the share of elements with |delta| <= rtol * rms(row) + rtol * |ref| (the elementwise
+    rtol = atol/rms = 2e-2 pass rate)."""
+    a, ref = a.double().reshape(-1, a.shape[-1]), ref.double().reshape(-1, ref.shape[-1])
+    d = (a - ref).abs()
+    row_rms = ref.pow(2).mean(-1, keepdim=True).sqrt().clamp(min=1e-30)
+    return {
+        "rel_rms": float((a - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt().clamp(min=1e-30)),
+        "max_over_row_rms": float((d.max(-1, keepdim=True).values / row_rms).max()),
+        "pass_rate": float((d <= rtol * row_rms + rtol * ref.abs()).double().mean()),
+        "max_abs": float(d.max()),
+    }

@@ -125,3 +125,40 @@ def test_synthetic_eval_items_are_reproducible_and_well_formed():
     n = (ids != 0).sum(-1)
     assert ((ids != 0).long().cumsum(-1)[torch.arange(3), n - 1] == n).all()          # no holes: tokens are a prefix
     assert (b1["enc_att_mask"] == (ids != 0).float()).all() and (n > 40).all()         # caption + two rounds + a question
+
+
+def test_sampling_seeds_differ_by_role_round_and_run_seed():
+    """questioner and teacher, every round, and every run seed get their own sampling stream."""
+    from gst_visdial_b200.models.visual_dialog_model import derive_seed
+    seeds = {derive_seed(base, role, idx) for base in (0, 1, 2**40 + 5) for role in ("q", "a", "enc_dec_q", "enc_dec_a") for idx in range(12)}
+    assert len(seeds) == 3 * 4 * 12
+    assert all(0 <= s < 2**64 for s in seeds)
+    assert derive_seed(0, "a", 3) == derive_seed(0, "a", 3)
+
+
+def test_jsonl_writer_raises_instead_of_deadlocking(tmp_path):
+    """a writer thread that died (here: records that cannot be serialised) must surface as an exception on the next
+    write / close even when the bounded queue is full - not as a blocked put."""
+    import threading
+    from gst_visdial_b200.io.output import JsonlWriter
+    w = JsonlWriter(str(tmp_path / "x.jsonl"), queue_depth=1)
+    w.write([{"ok": 1}])
+    w.write([{"bad": object()}])                      # json.dumps fails inside the thread
+    done = []
+
+    def hammer():
+        try:
+            for _ in range(50):
+                w.write([{"ok": 2}])
+        except Exception as e:                         # noqa: BLE001
+            done.append(e)
+
+    t = threading.Thread(target=hammer, daemon=True)
+    t.start()
+    t.join(timeout=20)
+    assert not t.is_alive(), "write() blocked on a dead writer thread"
+    assert done, "the writer's failure never reached the producer"
+    try:
+        w.close()
+    except Exception:                                  # noqa: BLE001 - close re-raises the writer's error
+        pass

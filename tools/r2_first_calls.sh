@@ -21,13 +21,13 @@ case "${1:-validate}" in
     ;;
   ab)
     # same-box A/B of every opt-in switch on the bench workload (3 streams) and on one single-stream round
-    for cfg in "X=0" "GSTVD_GEMM_2CTA=1" "GSTVD_GEMM_2CTA=256" "GSTVD_GEMM_2CTA=1 GSTVD_GEMM_2CTA_HM=1" "GSTVD_FUSE_LN=16" "GSTVD_FUSE_LN=16 GSTVD_FUSE_LN_SMALL=1" "GSTVD_GEMM_SPLITK=1" "GSTVD_GEMM_SPLITK=2" "GSTVD_GEMM_SKINNY_BN=64" "GSTVD_GEMM_SKINNY_BN=128" "GSTVD_GEMM_SKINNY_BN=64 GSTVD_GEMM_WIDE_BN=128" "GSTVD_GEMM_WIDE_BN=128" "GSTVD_ENC_FORK=1" "GSTVD_SELF_ANC=0" "GSTVD_SELF_V2=0 GSTVD_SELF_ANC=0"; do
+    for cfg in "X=0" "GSTVD_GEMM_2CTA=1" "GSTVD_GEMM_2CTA=1 GSTVD_GEMM_2CTA_HM=1" "GSTVD_FUSE_LN=16 GSTVD_FUSE_LN_SMALL=1" "GSTVD_GEMM_SPLITK=1" "GSTVD_GEMM_SKINNY_BN=64" "GSTVD_GEMM_SKINNY_BN=128" "GSTVD_GEMM_WIDE_BN=128" "GSTVD_ENC_FORK=1"; do
       echo "== $cfg"
       env $cfg timeout 120 python bench.py --steps 4 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1
       env $cfg timeout 60 python tools/profile_round.py --hist 150 2>&1 | tail -2
     done | tee gpurun_out/r2_ab.log
     # streams in flight with the default kernels (3 was the optimum before the late round-1 kernels)
-    for n in 2 4; do
+    for n in 1 2; do
       echo "== --streams $n"
       timeout 120 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --streams $n 2>/dev/null | tail -1
     done | tee -a gpurun_out/r2_ab.log
