@@ -61,9 +61,13 @@ template <int BN, int EW> struct TileCfg {
   static constexpr int kStageWords = 32 * 33;                   // per epilogue warp: 32 rows x 32 words, padded rows
   // wide: 33 KB = 4 x 8 KB (bf16) / 2 x 16 KB (fp32) TMA-store tiles, or 8 generic tiles; skinny: none (direct row stores only)
   static constexpr int kStagingBytes = kSkinny ? 0 : 8 * kStageWords * 4;
-  static constexpr int kLnVecBytes = EW * 4 * 32 * 4;           // deferred-LayerNorm epilogue: per warp, four 32-float column vectors
+  // deferred-LayerNorm epilogue: per warp, four 32-float column vectors - inside the (then unused) staging tiles of the wide
+  // configurations, appended to the allocation of the skinny one (LN instantiations only)
+  static constexpr int kLnVecBytes = EW * 4 * 32 * 4;
+  static constexpr int kLnVecExtra = kSkinny ? kLnVecBytes : 0;
+  static_assert(kSkinny || kLnVecBytes <= 8 * 32 * 33 * 4, "column vectors must fit the staging area");
   static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kBarBytes + kStagingBytes + 1024;   // +1024: alignment slack; LN kernels add kLnVecBytes
-  static_assert(!kSkinny || 2 * (kSmemBytes + kLnVecBytes + 1024) <= 233472, "skinny configuration must fit two CTAs per SM");
+  static_assert(!kSkinny || 2 * (kSmemBytes + kLnVecExtra + 1024) <= 233472, "skinny configuration must fit two CTAs per SM");
 };
 
 // Epilogue of one W-column block of this warp's 32 accumulator rows: TMEM -> registers (thread = row) -> + bias,
@@ -332,7 +336,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const uint32_t b_base = base + kStages * Cfg::kABytes;
   const uint32_t stage_base = b_base + kStages * Cfg::kBBytes;   // epilogue staging (1024-byte aligned: TMA-store source)
   const uint32_t bar_base = stage_base + Cfg::kStagingBytes;
-  const uint32_t lnvec_base = bar_base + Cfg::kBarBytes;         // deferred-LayerNorm column vectors (per epilogue warp; LN kernels only)
+  const uint32_t lnvec_base = Cfg::kSkinny ? bar_base + Cfg::kBarBytes : stage_base;   // deferred-LayerNorm column vectors (LN kernels only)
   // barrier layout: full[kStages] | empty[kStages] | tmem_full[2] | tmem_empty[2] | tmem base address (u32)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -704,7 +708,7 @@ void launch_cfg(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
   using Cfg = TileCfg<BN, EW>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EW, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes + (LN ? Cfg::kLnVecBytes : 0));
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EW, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes + (LN ? Cfg::kLnVecExtra : 0));
     if (e != cudaSuccess) throw std::runtime_error(std::string("gemm_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     attr_set = true;
   }
@@ -755,7 +759,7 @@ void launch_cfg(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
   }
   const int slots = Cfg::kSkinny ? 2 * num_sms : num_sms;      // resident CTAs: the kernel is persistent over the remaining tiles
   const int grid = tiles < slots ? tiles : slots;
-  launch_k(gemm_tc_kernel<BN, EW, LN>, dim3(grid), dim3(Cfg::kThreads), (size_t)(Cfg::kSmemBytes + (LN ? Cfg::kLnVecBytes : 0)), stream, *ma_ptr, mb, *mc, a);
+  launch_k(gemm_tc_kernel<BN, EW, LN>, dim3(grid), dim3(Cfg::kThreads), (size_t)(Cfg::kSmemBytes + (LN ? Cfg::kLnVecExtra : 0)), stream, *ma_ptr, mb, *mc, a);
 }
 
 }  // namespace
