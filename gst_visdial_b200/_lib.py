@@ -83,6 +83,7 @@ SYMBOLS = [
     ("gstvd_op_beam_step", c_int, [_P, _P, c_int64, _P, _P, _P, _P]),
     ("gstvd_op_beam_end", c_int, [_P, _P, _P, _P]),
     ("gstvd_op_sample", c_int, [_P, c_int, _P, c_int64, POINTER(GstvdGenParams), _P, _P, c_int, _P, c_int, c_int, _P, _P]),
+    ("gstvd_cross_key_counts", c_int, [_P, c_int, _P, _P]),
     ("gstvd_launch_count", c_int64, [_P]),
     ("gstvd_profile_gemm", c_int, [_P, c_int, c_int]),
     ("gstvd_profile_read", c_int, [_P, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64)]),

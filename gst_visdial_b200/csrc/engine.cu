@@ -1035,6 +1035,15 @@ int gstvd_splice(gstvd_ctx* c, int B, int Lt, int Lu, int64_t* enc_input_ids, in
   });
 }
 
+int gstvd_cross_key_counts(gstvd_ctx* c, int B, int32_t* out, void* stream) {
+  if (!c || !out) return GSTVD_ERR_INVALID;
+  return guarded(c, [&] {
+    if (c->dec_layers == 0) throw StateError("cross_key_counts: encoder-only context");
+    if (B < 1 || B != c->cross_B) throw StateError("cross_key_counts: B must equal the batch of the last gstvd_prefill_cross");
+    CUDA_CHECK(cudaMemcpyAsync(out, c->cross_len.p, (size_t)B * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  });
+}
+
 int64_t gstvd_launch_count(const gstvd_ctx* c) { return c ? c->launches : -1; }
 
 int gstvd_profile_gemm(gstvd_ctx* c, int enable, int min_rows) {

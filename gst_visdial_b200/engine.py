@@ -89,6 +89,16 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.gstvd_launch_count(self.ctx))
 
+    def decode_geometry(self, B=None):
+        """Measurement aid: the sizes bench.py's decode-step roofline is computed from, for the resident cross K/V of ``B`` images."""
+        d = self.dec_cfg
+        out = dict(hidden=int(d.hidden_size), layers=int(d.num_hidden_layers), vocab=int(d.vocab_size), ffn=int(d.intermediate_size))
+        B = int(B or self.max_batch)
+        counts = torch.empty(B, dtype=torch.int32, device=self.device)
+        check(self.ctx, self.lib.gstvd_cross_key_counts(self.ctx, B, _ptr(counts), self._stream()))
+        out["cross_keys_total"] = int(counts.sum().item())
+        return out
+
     def profile_gemm(self, enable: bool, min_rows: int = 0):
         check(self.ctx, self.lib.gstvd_profile_gemm(self.ctx, int(enable), int(min_rows)))
 

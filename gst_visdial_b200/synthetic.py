@@ -77,3 +77,75 @@ def synthetic_utterance(index: int, rnd: int, vocab_size: int = 30522, max_len: 
     out[: n - 1] = _rand_tokens(n - 1, vocab_size, g)
     out[n - 1] = SEP
     return out
+
+
+def _append(row_ids, row_seg, pos, utt, seg_value):
+    """Appends the non-zero ids of ``utt`` at ``pos`` (generate.py:148-160 without the overflow case: callers keep rows short)."""
+    n = int((utt != 0).sum())
+    row_ids[pos:pos + n] = utt[:n]
+    if seg_value is not None:
+        row_seg[pos:pos + n] = seg_value
+    return pos + n
+
+
+def synthetic_history_batch(start: int, count: int, vocab_size: int = 30522, v_feature_size: int = 2048, max_seq_len: int = 256,
+                            rounds=None, seed: int = 1234):
+    """``synthetic_batch`` whose histories already hold ``rounds[i]`` question / answer rounds (questions keep segment 0, answers get
+    segment 1 and no [SEP], like generate.py:148-160,214-228 leaves them): the contexts of BASELINE config 4.  Adds
+    ``hist_len_bound`` (int64 [1]): the longest history of the batch, known on the host without a device read."""
+    b = synthetic_batch(start, count, vocab_size, v_feature_size, max_seq_len, seed=seed)
+    ids, seg = b["enc_input_ids"], b["enc_segments"]
+    longest = 0
+    for i in range(count):
+        pos = int((ids[i] != 0).sum())
+        for r in range(int(rounds[i]) if rounds is not None else 0):
+            q = synthetic_utterance(start + i, 2 * r, vocab_size)
+            a = synthetic_utterance(start + i, 2 * r + 1, vocab_size)
+            a = a.masked_fill(a == SEP, 0)
+            if pos + int((q != 0).sum()) + int((a != 0).sum()) > max_seq_len:
+                break
+            pos = _append(ids[i], seg[i], pos, q, None)
+            pos = _append(ids[i], seg[i], pos, a, 1)
+        longest = max(longest, pos)
+    b["enc_att_mask"] = (ids != 0).float()
+    b["hist_len_bound"] = torch.tensor([longest], dtype=torch.int64)
+    return b
+
+
+def synthetic_candidate_batch(start: int, items: int, candidates: int = 100, vocab_size: int = 30522, v_feature_size: int = 2048,
+                              max_seq_len: int = 256, seed: int = 1234):
+    """BASELINE config 5 in the shape of evaluate_disc.py:66-83 / dataloader_visdial_disc.py:320-323: every item is one
+    (image, caption, r ~ U{1..10} rounds of history, question) with ``candidates`` answer options; each option is appended to the
+    text stream, so every candidate is its own ``max_seq_len``-token encoder input.  Segments alternate per utterance
+    (utils/data_utils.py:57), the attention mask covers positions up to the last [SEP] (train_disc.py:97-99).
+    Returns image tensors per ITEM ([items, 37, ...]) and token tensors per candidate ([items, candidates, max_seq_len])."""
+    feats, locs = [], []
+    tokens = torch.zeros(items, candidates, max_seq_len, dtype=torch.int64)
+    segments = torch.zeros(items, candidates, max_seq_len, dtype=torch.int64)
+    longest = 0
+    for i in range(items):
+        feat, loc, g = synthetic_image(start + i, v_feature_size, 36, seed)
+        feats.append(feat); locs.append(loc)
+        n = int(torch.randint(8, 39, (1,), generator=g))
+        row = torch.zeros(max_seq_len, dtype=torch.int64)
+        sg = torch.zeros(max_seq_len, dtype=torch.int64)
+        row[0] = CLS
+        row[1:1 + n] = _rand_tokens(n, vocab_size, g)
+        row[1 + n] = SEP
+        pos, cur_seg = n + 2, 1                               # caption utterance: segment 0 ... alternate from here on
+        r = int(torch.randint(1, 11, (1,), generator=g))
+        for u in range(2 * (r - 1) + 1):                      # (r - 1) complete rounds, then the current question
+            utt = synthetic_utterance(start + i, u, vocab_size)
+            if pos + int((utt != 0).sum()) + 14 > max_seq_len:
+                break
+            pos = _append(row, sg, pos, utt, cur_seg)
+            cur_seg ^= 1
+        for c in range(candidates):
+            cand = synthetic_utterance((start + i) * 131 + c, 500 + c, vocab_size)
+            tokens[i, c] = row
+            segments[i, c] = sg
+            end = _append(tokens[i, c], segments[i, c], pos, cand, cur_seg)
+            longest = max(longest, end)
+    mask = (tokens != 0).float()
+    return {"image_feat": torch.stack(feats), "image_loc": torch.stack(locs), "image_mask": torch.ones(items, 37),
+            "tokens": tokens, "segments": segments, "mask": mask, "hist_len_bound": torch.tensor([longest], dtype=torch.int64)}

@@ -227,6 +227,10 @@ int gstvd_op_deferred_ln_chain(gstvd_ctx* ctx, int M, int N, int K1, const float
  * compute dtype), else reads it back.  Lets the tests check gstvd_reorder_cache against index_select(0, beam_idx) directly. */
 int gstvd_debug_self_cache(gstvd_ctx* ctx, int write, int B, int K, int layer, int kv, float* buf, void* stream);
 
+/* Measurement aid (bench.py's decode-step roofline): out int32 [B] (device) = keys of each image's resident cross-attention K/V
+ * that a decode step fetches (last unmasked key + 1, computed at gstvd_prefill_cross). */
+int gstvd_cross_key_counts(gstvd_ctx* ctx, int B, int32_t* out, void* stream);
+
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t gstvd_launch_count(const gstvd_ctx* ctx);
 
