@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libgstvd.so")
-SOURCES = ["engine.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_ln.cu", "gemm_splitk.cu", "gemm_simt.cu", "norm.cu", "attention.cu", "attention_mma.cu", "decode.cu", "cross_tma.cu", "select.cu"]
+SOURCES = ["engine.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "norm.cu", "attention.cu", "attention_mma.cu", "decode.cu", "cross_tma.cu", "select.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-diag-suppress", "177"]
 

@@ -20,7 +20,6 @@ GSTVD_FLAG_NO_CUDA_GRAPH = 1
 GSTVD_FLAG_DEBUG_SIMT_GEMM = 2
 GSTVD_FLAG_GENERIC_ATTENTION = 4
 GSTVD_FLAG_NO_PDL = 8
-GSTVD_FLAG_SHARED_SM_GEMM = 16
 GSTVD_MAX_TOP_K = 16
 
 STATUS_NAMES = {0: "OK", -1: "INVALID", -2: "CUDA", -3: "UNSUPPORTED", -4: "STATE"}
@@ -75,7 +74,6 @@ SYMBOLS = [
     ("gstvd_splice", c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, c_int, _P, _P]),
     ("gstvd_op_linear", c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P]),
     ("gstvd_op_add_layernorm", c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
-    ("gstvd_op_linear_add_layernorm", c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P]),
     ("gstvd_op_attention", c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_float, c_int, _P, _P]),
     ("gstvd_op_deferred_ln_chain", c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("gstvd_debug_self_cache", c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),

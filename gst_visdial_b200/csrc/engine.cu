@@ -66,10 +66,13 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
 
+// Shapes and selection parameters only: the n-gram blocking history is copied into context-owned buffers before a replay, so the
+// caller's tensor addresses are not part of the key (a caching allocator hands out a new address per batch).
 struct GraphKey {
-  int B, K, mode, T, top_k, ngram, Lh; float temperature, top_p; const void* hist_ids; const void* hist_seg;
+  int B, K, mode, T, top_k, ngram, Lh, Le; float temperature, top_p;
   bool operator<(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) < 0; }
 };
+constexpr size_t kMaxGraphs = 24;      // least-recently-used graphs beyond this are destroyed (an 18-step graph holds ~2k kernel nodes)
 
 }  // namespace
 
@@ -120,16 +123,16 @@ struct gstvd_ctx {
   // beam op-test state
   int op_B = 0, op_K = 0, op_T = 0;
 
-  std::map<GraphKey, cudaGraphExec_t> graphs;
-  std::map<GraphKey, int64_t> graph_kernels;          // kernels per replay, counted while the step was captured
+  struct GraphEntry { cudaGraphExec_t exec; int64_t kernels; uint64_t last_use; };   // kernels per replay, counted during capture
+  std::map<GraphKey, GraphEntry> graphs;
+  uint64_t graph_clock = 0;
+  DevBuf hist_ids_own, hist_seg_own;                  // int64 [B_max, Lt_max]: n-gram blocking history read by captured graphs
   // optional event profiling of the tcgen05 GEMM launches (bench.py roofline): one event pair per launch
   bool profiling = false; int prof_min_rows = 0;
   struct ProfRec { cudaEvent_t a, b; double flops, bytes; };
   std::vector<ProfRec> prof_pool; size_t prof_used = 0;
   cudaStream_t own_stream = nullptr;     // decode steps run (and are graph-captured) here: the caller may be on the legacy stream
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-  cudaStream_t side_stream = nullptr;    // image stream of the encoder when it runs beside the text stream (GSTVD_ENC_FORK)
-  cudaEvent_t ev_main = nullptr, ev_side = nullptr;
 
   size_t act_bytes(size_t elems) const { return elems * esz; }
 };
@@ -322,6 +325,7 @@ void alloc_workspace(gstvd_ctx* c) {
     c->cross_len.alloc(B * 4);
     c->sel_val.alloc(R * kSelMax * 4); c->sel_idx.alloc(R * kSelMax * 4); c->logz.alloc(R * 4);
     c->ban_tokens.alloc(B * Lt * 4); c->ban_count.alloc(B * 4);
+    c->hist_ids_own.alloc(B * Lt * 8); c->hist_seg_own.alloc(B * Lt * 8);
     c->prefix.alloc(B * (T + 1) * 4); c->seq.alloc(B * T * 4);
     c->beam_scores.alloc(B * K * 4); c->beam_tokens.alloc(2 * B * K * T * 4); c->cur_tokens.alloc(R * 4);
     c->beam_idx.alloc(B * K * 4); c->beam_done.alloc(B); c->hyp_score.alloc(B * (K + 1) * 8);
@@ -355,7 +359,7 @@ struct Exec {
         const bool prof = c->profiling && M >= c->prof_min_rows && c->prof_used < c->prof_pool.size() &&
                           cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone;
         if (prof) cudaEventRecord(c->prof_pool[c->prof_used].a, s);
-        c->launches += launch_gemm_tc(a, c->num_sms, s, (c->cfg.flags & GSTVD_FLAG_SHARED_SM_GEMM) != 0);
+        c->launches += launch_gemm_tc(a, c->num_sms, s);
         if (prof) {
           auto& r = c->prof_pool[c->prof_used++];
           cudaEventRecord(r.b, s);
@@ -382,16 +386,8 @@ struct Exec {
   void add_ln(const void* x, const void* res, const LNp& l, void* y, int rows) {
     c->launches += launch_add_layernorm(dt(), rows, l.n, x, l.n, res, l.n, l.g, l.b, y, l.n, s);
   }
-  // y = LN(A L^T + bias + res): the fused cluster kernel when enabled (env GSTVD_FUSE_LN) and applicable, else GEMM into tmp + add_ln
+  // y = LN(A L^T + bias + res): GEMM into tmp, then add + LayerNorm (the bf16 decode step defers the LayerNorm instead: gemm_ln)
   void gemm_add_ln(const void* A, int64_t lda, const Linear& L, const void* res, const LNp& l, void* tmp, void* y, int M) {
-    const int mode = gemm_ln_mode();
-    if (mode != 0 && c->dtype == kBF16 && !(c->cfg.flags & GSTVD_FLAG_DEBUG_SIMT_GEMM) && l.n == L.out &&
-        gemm_ln_tc_supported(M, L.out, L.in, A, lda, L.w16, L.in, res, l.n, y, l.n)) {
-      GemmArgs a;
-      a.A = A; a.lda = lda; a.W = L.w16; a.ldw = L.in; a.bias = L.b; a.M = M; a.N = L.out; a.K = L.in;
-      c->launches += launch_gemm_ln_tc(a, res, l.n, l.g, l.b, 1e-12f, y, l.n, mode, s);
-      return;
-    }
     gemm(A, lda, L, tmp, L.out, M);
     add_ln(tmp, res, l, y, M);
   }
@@ -429,23 +425,18 @@ void self_layer_fwd(Exec& X, const SelfLayer& L, void* x, void* y, void* qkv, vo
   (void)c;
 }
 
-// XT runs the text-stream work, XV the image-stream work.  They are the same Exec unless the encoder is forked over two CUDA
-// streams (do_encode); `exchange` then orders the two streams against each other around the co-attention pair: both attentions
-// read BOTH streams' q|k|v buffers, and neither stream may overwrite its buffer (next layer's projection) while the other's
-// attention still reads it.
-template <typename Exchange>
-void conn_layer_fwd(Exec& XT, Exec& XV, const ConnLayer& L, int B, int Lt, int Lv, const float* tmask, const float* vmask, Exchange&& exchange) {
+// XT runs the text-stream work, XV the image-stream work (the same Exec: running the image stream on a second CUDA stream was
+// measured slower once several batches are in flight, profiles/r2_switch_ab.txt).
+void conn_layer_fwd(Exec& XT, Exec& XV, const ConnLayer& L, int B, int Lt, int Lv, const float* tmask, const float* vmask) {
   gstvd_ctx* c = XT.c;
   const int H = c->H, Hv = c->Hv, Hb = c->Hb, D = Hb / c->heads_b, Mt = B * Lt, Mv = B * Lv;
   void *xt = c->xt.p, *yt = c->yt.p, *xv = c->xv.p, *yv = c->yv.p;
   void *qv = c->qkv_v.p, *qt = c->qkv_t.p;
   XV.gemm(xv, Hv, L.qkv1, qv, 3 * Hb, Mv);      // query1 | key1 | value1  (image stream)
   XT.gemm(xt, H, L.qkv2, qt, 3 * Hb, Mt);       // query2 | key2 | value2  (text stream)
-  exchange();
   // text queries over image keys/values -> ctx_t ; image queries over text keys/values -> ctx_v  (:671-710)
   XT.attention(qt, 3 * Hb, Lt, XT.off(qv, Hb), XT.off(qv, 2 * Hb), 3 * Hb, Lv, c->ctx_t.p, Hb, B, c->heads_b, D, vmask, -10000.0f, 0);
   XV.attention(qv, 3 * Hb, Lv, XV.off(qt, Hb), XV.off(qt, 2 * Hb), 3 * Hb, Lt, c->ctx_v.p, Hb, B, c->heads_b, D, tmask, -10000.0f, 0);
-  exchange();
   // BertBiOutput with the contexts swapped into the opposite stream (:765, :732-744)
   XV.gemm(c->ctx_v.p, Hb, L.dense1, c->tmp_v.p, Hv, Mv);
   XV.add_ln(c->tmp_v.p, xv, L.ln1, yv, Mv);
@@ -503,20 +494,7 @@ void do_encode(gstvd_ctx* c, int B, int Lt, int Lv, const int64_t* ids, const in
   PdlScope pdl_scope(!(c->cfg.flags & GSTVD_FLAG_NO_PDL));
   if (Lt > c->cfg.max_position_embeddings) throw InvalidArg("encode: Lt exceeds max_position_embeddings");
   Exec X{c, s};
-  // The two streams of the ViLBERT encoder only meet in the co-attention of a connection layer (models/vilbert_dialog.py:831-905):
-  // with GSTVD_ENC_FORK=1 the image stream (2 368 rows at batch 64: half a wave of GEMM tiles) runs on a second CUDA stream beside
-  // the text stream and fills the SMs its wave tails leave idle.  EXPERIMENTAL (host-side change only, same kernels): not yet timed.
-  const char* fork_env = getenv("GSTVD_ENC_FORK");
-  const bool fork = fork_env != nullptr && atoi(fork_env) != 0 && c->side_stream != nullptr && s != c->side_stream;
-  Exec XV{c, fork ? c->side_stream : s};
-  auto exchange = [&] {                       // each stream waits for everything the other has enqueued so far
-    if (!fork) return;
-    CUDA_CHECK(cudaEventRecord(c->ev_main, s));
-    CUDA_CHECK(cudaEventRecord(c->ev_side, c->side_stream));
-    CUDA_CHECK(cudaStreamWaitEvent(s, c->ev_side, 0));
-    CUDA_CHECK(cudaStreamWaitEvent(c->side_stream, c->ev_main, 0));
-  };
-  exchange();                                 // fork: the side stream starts after whatever precedes this call on `s`
+  Exec& XV = X;                               // image-stream work
   const int H = c->H, Hv = c->Hv, Mt = B * Lt, Mv = B * Lv;
   c->launches += launch_embed_text(c->dtype, Mt, Lt, H, ids, seg, nullptr, 0, c->word, c->pos, c->type, c->type_ext,
                                    c->cfg.type_vocab_size, c->emb_ln.g, c->emb_ln.b, c->xt.p, s);
@@ -535,12 +513,11 @@ void do_encode(gstvd_ctx* c, int B, int Lt, int Lv, const int64_t* ids, const in
     const int v_end = c->cfg.v_biattention_id[n], t_end = c->cfg.t_biattention_id[n];
     for (int i = v_start; i < v_end; ++i) image_layer(i);
     for (int i = t_start; i < t_end; ++i) text_layer(i);
-    conn_layer_fwd(X, XV, c->c_layers[n], B, Lt, Lv, att, imask, exchange);
+    conn_layer_fwd(X, XV, c->c_layers[n], B, Lt, Lv, att, imask);
     v_start = v_end; t_start = t_end;
   }
   for (int i = v_start; i < c->cfg.v_num_hidden_layers; ++i) image_layer(i);
   for (int i = t_start; i < c->cfg.num_hidden_layers; ++i) text_layer(i);
-  exchange();                                 // join: everything below reads both streams' results on `s`
 
   if (out_t) c->launches += launch_cast_to_f32(c->dtype, c->xt.p, out_t, (int64_t)Mt * H, s);
   if (out_v) c->launches += launch_cast_to_f32(c->dtype, c->xv.p, out_v, (int64_t)Mv * Hv, s);
@@ -632,8 +609,7 @@ void decode_step(gstvd_ctx* c, const DecodeGeom& g, const gstvd_gen_params& gp, 
   // layer store raw sums + partial row statistics, their consumers normalise on the fly (GemmArgs::fold_* / res_*), and one
   // ln_apply_stats launch materialises the last layer's output for the LM head.  36 launches and 36 dependent stages per step less.
   static const bool defer_env = [] { const char* e = getenv("GSTVD_DEFER_LN"); return e == nullptr || atoi(e) != 0; }();
-  const bool defer = defer_env && c->fold_ready && c->dtype == kBF16 && !(c->cfg.flags & GSTVD_FLAG_DEBUG_SIMT_GEMM) && M <= 512 &&
-                     gemm_ln_mode() == 0;
+  const bool defer = defer_env && c->fold_ready && c->dtype == kBF16 && !(c->cfg.flags & GSTVD_FLAG_DEBUG_SIMT_GEMM) && M <= 512;
   if (defer) {
     float2 *st1 = (float2*)c->st1.p, *st2 = (float2*)c->st2.p, *st3 = (float2*)c->st3.p;
     void *x1 = c->da.p, *x2 = c->db.p, *x3 = c->dtmp.p;
@@ -735,16 +711,28 @@ void do_generate(gstvd_ctx* c, int B, const gstvd_gen_params& gp, const int64_t*
     std::memset(&key, 0, sizeof key);
     key.B = B; key.K = K; key.mode = gp.mode; key.T = T; key.top_k = gp.top_k; key.ngram = gp.ngram_blocking_size; key.Lh = Lh;
     key.temperature = gp.temperature; key.top_p = gp.top_p;
-    key.hist_ids = gp.ngram_blocking_size > 0 ? hist_ids : nullptr; key.hist_seg = gp.ngram_blocking_size > 0 ? hist_seg : nullptr;
-    // the cross cache geometry (Le) is part of the captured launch parameters
-    key.Lh = key.Lh * 1024 + c->cross_Le;
+    key.Le = c->cross_Le;                    // the cross cache geometry is part of the captured launch parameters
+    const int64_t* g_ids = hist_ids; const int64_t* g_seg = hist_seg;
+    if (gp.ngram_blocking_size > 0) {
+      // the graph reads the history from the context's own buffers: refresh them (device-to-device, ordered on this stream)
+      CUDA_CHECK(cudaMemcpyAsync(c->hist_ids_own.p, hist_ids, (size_t)B * Lh * 8, cudaMemcpyDeviceToDevice, s));
+      CUDA_CHECK(cudaMemcpyAsync(c->hist_seg_own.p, hist_seg, (size_t)B * Lh * 8, cudaMemcpyDeviceToDevice, s));
+      g_ids = (const int64_t*)c->hist_ids_own.p; g_seg = (const int64_t*)c->hist_seg_own.p;
+    }
     auto it = c->graphs.find(key);
     if (it == c->graphs.end()) {
+      if (c->graphs.size() >= kMaxGraphs) {  // evict the least recently used graph
+        auto victim = c->graphs.begin();
+        for (auto j = c->graphs.begin(); j != c->graphs.end(); ++j) if (j->second.last_use < victim->second.last_use) victim = j;
+        CUDA_CHECK(cudaStreamSynchronize(s));             // it may still be executing on this stream
+        cudaGraphExecDestroy(victim->second.exec);
+        c->graphs.erase(victim);
+      }
       const int64_t before = c->launches;
       cudaGraph_t graph;
       CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
       try {
-        for (int t = 0; t < T; ++t) decode_step(c, g, gp, hist_ids, hist_seg, Lh, s, t);   // all T steps in ONE graph: no host round trip between steps
+        for (int t = 0; t < T; ++t) decode_step(c, g, gp, g_ids, g_seg, Lh, s, t);   // all T steps in ONE graph: no host round trip between steps
       } catch (...) {
         cudaGraph_t dead; cudaStreamEndCapture(s, &dead);
         throw;
@@ -753,12 +741,12 @@ void do_generate(gstvd_ctx* c, int B, const gstvd_gen_params& gp, const int64_t*
       cudaGraphExec_t exec;
       CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
       CUDA_CHECK(cudaGraphDestroy(graph));
-      it = c->graphs.emplace(key, exec).first;
-      c->graph_kernels[key] = c->launches - before;   // kernels per replay = what the captured steps enqueued
+      it = c->graphs.emplace(key, gstvd_ctx::GraphEntry{exec, c->launches - before, 0}).first;
       c->launches = before;                           // capture itself launches nothing
     }
-    CUDA_CHECK(cudaGraphLaunch(it->second, s));
-    c->launches += c->graph_kernels[key];
+    it->second.last_use = ++c->graph_clock;
+    CUDA_CHECK(cudaGraphLaunch(it->second.exec, s));
+    c->launches += it->second.kernels;
   }
   if (gp.mode == GSTVD_SELECT_BEAM) c->launches += launch_beam_finalize(beam_buffers(c), B, K, T, 102, out_ids, out_scores, s);
   else c->launches += launch_sample_finalize(B, T, 102, (const int32_t*)c->seq.p, out_ids, s);
@@ -904,9 +892,6 @@ int gstvd_create(const gstvd_config* cfg, int device, gstvd_ctx** out) {
     CUDA_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
-    CUDA_CHECK(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
-    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
-    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
     CUDA_CHECK(cudaDeviceSynchronize());
   });
   if (rc != GSTVD_OK) { if (c) gstvd_destroy(c); return rc; }
@@ -919,21 +904,18 @@ void gstvd_destroy(gstvd_ctx* c) {
   int prev = -1; cudaGetDevice(&prev);
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second.exec);
   DevBuf* bufs[] = {&c->mat32, &c->mat16, &c->vec32, &c->xt, &c->yt, &c->xv, &c->yv, &c->qkv_t, &c->qkv_v, &c->ctx_t, &c->ctx_v, &c->tmp_t,
                     &c->tmp_v, &c->ffn_t, &c->ffn_v, &c->feat_cast, &c->fused, &c->pool, &c->fused_mask, &c->dh, &c->da, &c->db, &c->dqkv,
                     &c->dctx, &c->dtmp, &c->dffn, &c->dqc, &c->logits, &c->cross_cache, &c->self_cache, &c->cross_len, &c->labels, &c->sel_val, &c->sel_idx,
                     &c->logz, &c->ban_tokens, &c->ban_count, &c->prefix, &c->seq, &c->beam_scores, &c->beam_tokens, &c->cur_tokens,
                     &c->beam_idx, &c->beam_done, &c->hyp_score, &c->hyp_len, &c->hyp_tokens, &c->hyp_count, &c->hyp_worst, &c->d_step, &c->d_seed, &c->anc, &c->fold16, &c->foldvec,
-                    &c->st1, &c->st2, &c->st3};
+                    &c->st1, &c->st2, &c->st3, &c->hist_ids_own, &c->hist_seg_own};
   for (DevBuf* b : bufs) b->release();
   for (auto& r : c->prof_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (c->ev_in) cudaEventDestroy(c->ev_in);
   if (c->ev_out) cudaEventDestroy(c->ev_out);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
-  if (c->ev_main) cudaEventDestroy(c->ev_main);
-  if (c->ev_side) cudaEventDestroy(c->ev_side);
-  if (c->side_stream) cudaStreamDestroy(c->side_stream);
   delete c;
   if (prev >= 0) cudaSetDevice(prev);
 }
@@ -972,7 +954,7 @@ int gstvd_finalize_weights(gstvd_ctx* c, void* stream) {
       assign_w16(c);
       prepare_fold(c, s);
     }
-    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second.exec);
     c->graphs.clear();
     c->finalized = true;
   });
@@ -1141,29 +1123,6 @@ int gstvd_op_add_layernorm(gstvd_ctx* c, int dtype, int rows, int width, const f
       c->launches += launch_cast_to_f32(kBF16, y16, y, n, s);
       CUDA_CHECK(cudaStreamSynchronize(s));
     }
-  });
-}
-
-int gstvd_op_linear_add_layernorm(gstvd_ctx* c, int M, int K, const float* a, const float* w, const float* bias, const float* residual,
-                                  const float* gamma, const float* beta, int cluster, float* y, void* stream) {
-  if (!c) return GSTVD_ERR_INVALID;
-  return guarded(c, [&] {
-    cudaStream_t s = (cudaStream_t)stream;
-    const int N = 768;
-    if (M < 1 || K < 1 || K % 256 != 0) throw InvalidArg("op_linear_add_layernorm: K must be a positive multiple of 256");
-    if (!a || !w || !gamma || !beta || !y) throw InvalidArg("op_linear_add_layernorm: NULL buffer");
-    if (cluster != 8 && cluster != 16) throw InvalidArg("op_linear_add_layernorm: cluster must be 8 or 16");
-    Scratch sc;
-    void* a16 = sc.get((size_t)M * K * 2); void* w16 = sc.get((size_t)N * K * 2);
-    void* r16 = residual ? sc.get((size_t)M * N * 2) : nullptr; void* y16 = sc.get((size_t)M * N * 2);
-    c->launches += launch_cast_f32_to(kBF16, a, a16, (int64_t)M * K, s);
-    c->launches += launch_cast_f32_to(kBF16, w, w16, (int64_t)N * K, s);
-    if (residual) c->launches += launch_cast_f32_to(kBF16, residual, r16, (int64_t)M * N, s);
-    GemmArgs g;
-    g.A = a16; g.lda = K; g.W = w16; g.ldw = K; g.bias = bias; g.M = M; g.N = N; g.K = K;
-    c->launches += launch_gemm_ln_tc(g, r16, N, gamma, beta, 1e-12f, y16, N, cluster, s);
-    c->launches += launch_cast_to_f32(kBF16, y16, y, (int64_t)M * N, s);
-    CUDA_CHECK(cudaStreamSynchronize(s));
   });
 }
 

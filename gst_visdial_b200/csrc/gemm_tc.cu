@@ -20,8 +20,8 @@
 // Both operands are K-major ("TN"), which is the layout of activations [rows, features] and nn.Linear weights
 // [out, in], so no transposes are ever materialised.  TMA zero-fills out-of-range rows / k, so M, N, K need not be
 // multiples of the tile (K % 8 == 0 for the 16-byte stride rule).
-// Siblings built on the same helpers (gemm_tc.cuh): gemm_tc2.cu (CTA-pair tiles, cta_group::2) and gemm_ln.cu (cluster GEMM +
-// LayerNorm for the decode step).  This file also owns the tensor-map cache they share.
+// Sibling built on the same helpers (gemm_tc.cuh): gemm_tc2.cu (CTA-pair tiles, cta_group::2, for the large-M problems).  This file
+// also owns the tensor-map cache they share.
 #include <cuda.h>
 
 #include <algorithm>
@@ -786,7 +786,7 @@ const void* tma_map_rows3(const void* ptr, int D, int L, int64_t groups, int box
   return &cached_map(key, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream, bool shared_sm) {
+int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
   if (a_in.M <= 0 || a_in.N <= 0) return 0;
   static const int dbg_env = [] { const char* e = getenv("GSTVD_GEMM_DBG"); return e ? atoi(e) : 0; }();
   static const int bn_env = [] { const char* e = getenv("GSTVD_GEMM_BN"); return e ? atoi(e) : 0; }();
@@ -803,8 +803,7 @@ int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream, bool 
     else { if (a.stats_out != nullptr) throw std::runtime_error("gemm_tc: statistics are only written by 32-column tiles"); launch_cfg<64, kEpiWarpsWide, true>(a, num_sms, stream); }
     return 1;
   }
-  if (launch_gemm_splitk_if_selected(a, stream)) return 1;         // EXPERIMENTAL cluster split-K kernel for decode problems (env GSTVD_GEMM_SPLITK)
-  if (launch_gemm_tc2_if_selected(a, num_sms, stream)) return 1;   // EXPERIMENTAL CTA-pair kernel (env GSTVD_GEMM_2CTA)
+  if (launch_gemm_tc2_if_selected(a, num_sms, stream)) return 1;   // CTA-pair tiles (cta_group::2) where they measured faster: large M
   const int tiles_m = (a.M + BM - 1) / BM;
   int bn = 32;
   const int cand[4] = {256, 128, 64, 32};
@@ -833,7 +832,6 @@ int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream, bool 
   // Skinny (decode) problems whose output qualifies for direct row stores run the M = 64 configuration (two CTAs per SM):
   // 32-column tiles when they all fit the 2 x SMs resident slots, else 64-column tiles.
   static const int skinny_env = [] { const char* e = getenv("GSTVD_GEMM_SKINNY"); return e ? atoi(e) : -1; }();   // A/B aid: force 0 / 1
-  (void)shared_sm;                                         // kept in the signature: the M = 64 configuration is shared-SM by construction
   const bool skinny = skinny_env >= 0 ? skinny_env != 0 : true;
   {
     const int esz = a.out_f32 ? 4 : 2;
@@ -842,22 +840,6 @@ int launch_gemm_tc(const GemmArgs& a_in, int num_sms, cudaStream_t stream, bool 
                            getenv("GSTVD_GEMM_NO_TMA_STORE") == nullptr;
     if (skinny && direct_ok && a.K % BK == 0 && !bn_env) {
       const int tm64 = (a.M + 63) / 64;
-      // A/B aid (read per launch): GSTVD_GEMM_SKINNY_BN=64|128 widens the decode tiles.  The 32-column tiles are the fastest for one
-      // stream (most CTAs, least per-CTA bytes) but every one of the N/32 column tiles re-reads the 64 x K activation block through
-      // L2: 17.7 MB per 768 x 768 GEMM against 11.8 MB (64 columns) / 8.8 MB (128 columns) - and with several streams in flight
-      // the L2 -> SM fabric is the contended resource.  Not yet timed.
-      // GSTVD_GEMM_WIDE_BN=128|256 (N > 768 only: the QKV and FFN1 projections): 128-row tiles of that width instead of 64 columns -
-      // three row blocks re-read W instead of five, and half / a quarter as many column tiles re-read the activations
-      // (31.8 -> 21.2 MB for N = 2304, 42 -> 28.3 MB for N = 3072 at 128 columns).  Not yet timed.
-      if (const char* wide = getenv("GSTVD_GEMM_WIDE_BN")) {
-        const int w = atoi(wide);
-        if (a.N > 768 && (w == 128 || w == 256)) { if (w == 128) launch_cfg<128>(a, num_sms, stream); else launch_cfg<256>(a, num_sms, stream); return 1; }
-      }
-      if (const char* wenv = getenv("GSTVD_GEMM_SKINNY_BN")) {
-        const int w = atoi(wenv);
-        if (w == 128) { launch_cfg<128, kEpiWarpsSkinny>(a, num_sms, stream); return 1; }
-        if (w == 64) { launch_cfg<64, kEpiWarpsSkinny>(a, num_sms, stream); return 1; }
-      }
       static const int multi = [] { const char* e = getenv("GSTVD_GEMM_SKINNY_WAVES"); return e ? atoi(e) : 1; }();   // A/B aid
       if (tm64 * ((a.N + 31) / 32) <= 2 * num_sms * multi) { launch_cfg<32, kEpiWarpsSkinny>(a, num_sms, stream); return 1; }
       // wider outputs (N = 2304 / 3072 at M = 320) measured faster in the 128-row configuration with 16 epilogue warps

@@ -1,5 +1,4 @@
-// Device helpers shared by the tcgen05 GEMM family (gemm_tc.cu: single-CTA tiles, gemm_tc2.cu: CTA pairs, gemm_ln.cu: cluster
-// GEMM + LayerNorm): mbarrier / TMA / tcgen05 / cluster PTX wrappers, the UMMA descriptors, the TMA-store epilogue block, and
+// Device helpers shared by the tcgen05 GEMM family (gemm_tc.cu: single-CTA tiles, gemm_tc2.cu: CTA pairs): mbarrier / TMA / tcgen05 / cluster PTX wrappers, the UMMA descriptors, the TMA-store epilogue block, and
 // the interface of the host-side tensor-map cache.  sm_100a only.
 #pragma once
 #include <cuda.h>
@@ -304,10 +303,9 @@ const CUtensorMap& get_map_c(const void* ptr, int64_t rows, int64_t cols, int64_
 const CUtensorMap& get_map_a3(const void* ptr, int64_t K, int L, int B, int64_t ld);
 const CUtensorMap& get_map_hm3(const void* ptr, int D, int L, int64_t LBG, int box_cols);
 
-// CTA-pair kernel (gemm_tc2.cu): launches it and returns 1 when env GSTVD_GEMM_2CTA selects it for this problem, else returns 0.
+// CTA-pair kernel (gemm_tc2.cu): launches it and returns 1 when it is the faster configuration for this problem (large M, see
+// pick_pair_bn; env GSTVD_GEMM_2CTA=0 disables it, =128 / =256 force a pair tile width), else returns 0.
 int launch_gemm_tc2_if_selected(const GemmArgs& a, int num_sms, cudaStream_t stream);
-// Cluster split-K kernel for the decode projections (gemm_splitk.cu): same contract with env GSTVD_GEMM_SPLITK.
-int launch_gemm_splitk_if_selected(const GemmArgs& a, cudaStream_t stream);
 
 }  // namespace tc
 }  // namespace gstvd

@@ -1,4 +1,5 @@
-// CTA-pair tcgen05 GEMM (cta_group::2): 256 x BN tiles computed by two SMs of one TPC.  EXPERIMENTAL, see below.
+// CTA-pair tcgen05 GEMM (cta_group::2): 256 x BN tiles computed by two SMs of one TPC.  Default for the large-M throughput problems
+// (pick_pair_bn below); parity: tests/test_gpu_ops.py::test_linear_pair_bf16 and the model-level pair-GEMM tests.
 #include <algorithm>
 #include <cstdlib>
 #include <stdexcept>
@@ -15,9 +16,9 @@ namespace {
 // ------------------------------------------------------------------------------------------------------------
 // CTA-pair GEMM (tcgen05 cta_group::2) for the throughput problems (encoder / prefill / teacher-forced passes, M >= 1024).
 //
-// Why: with one CTA per 128 x 256 tile every SM pulls 48 KB of operands through L2 per 64-wide k-block, i.e. 106 GB/s per SM at
-// the full MMA rate - 15.7 TB/s over 148 SMs, above what L2 delivers (~12 TB/s): the single-CTA kernel is L2-bound at 57 % of the
-// measured bf16 peak.  A CTA pair (two SMs of one TPC, cluster of 2) computes a 256 x BN tile with ONE tcgen05.mma.cta_group::2
+// Why: with one CTA per 128 x 256 tile every SM pulls 48 KB of operands per 64-wide k-block (512 tensor-pipe cycles): 96 B / cycle
+// against the ~45-64 B / cycle one SM ingests (the decode GEMMs' main loops run at 86 GB/s per CTA whatever the grid size,
+// profiles/r2_gemm_phases.txt).  A CTA pair (two SMs of one TPC, cluster of 2) computes a 256 x BN tile with ONE tcgen05.mma.cta_group::2
 // per k-step issued by the leader: each CTA stages its own 128 rows of A and only HALF of the W tile (BN/2 rows) - the tensor
 // cores read the other half from the peer's shared memory - so the per-SM operand traffic drops to 32 KB per k-block (-33 %)
 // for the same math.
@@ -30,7 +31,7 @@ namespace {
 //   * each CTA's 16 epilogue warps drain their own 128 accumulator rows (bias / GELU / convert / TMA store, shared with the
 //     single-CTA kernel) and arrive on the leader's accumulator-empty barrier (remote mbarrier.arrive for the follower);
 //   * TMEM is allocated / freed with the cta_group::2 forms by warp 1 of both CTAs.
-// EXPERIMENTAL: selected only with env GSTVD_GEMM_2CTA=1 until it has been validated on the GPU.
+// Measured (profiles/r2_gemm_pair_vs_single.txt): +2 ... +8 % over the single-CTA kernel from M = 12 288 on, slower below.
 template <int BN> struct Tile2Cfg {
   static constexpr int kBMc = BM;                               // rows per CTA; the pair tile has 2 * BM rows
   static constexpr int kBH = BN / 2;                            // W rows staged by each CTA
@@ -298,38 +299,30 @@ void launch_cfg2(const GemmArgs& a_in, int num_sms, cudaStream_t stream) {
   if (e != cudaSuccess) throw std::runtime_error(std::string("gemm_tc2: launch failed: ") + cudaGetErrorString(e));
 }
 
-// CTA-pair configuration for this problem, or 0: needs the plain [M, N] TMA-store epilogue and enough rows to fill pair tiles.
+// CTA-pair configuration for this problem, or 0.  Needs the plain [M, N] (or head-major) TMA-store epilogue and enough rows to
+// fill pair tiles.  Selection rule from a same-box sweep over the encoder shapes (profiles/r2_gemm_pair_vs_single.txt): the
+// 256-column pair tile is 2-8 % faster than the single-CTA 128 x 256 tile from M = 12 288 on (and from M = 8 192 for the wide / deep
+// problems), slower below (fewer, larger tiles quantise worse); the 128-column pair tile never wins.
+// env GSTVD_GEMM_2CTA: 0 = never, 128 / 256 = force that pair width wherever the kernel applies (tests), unset / 1 = the rule.
 int pick_pair_bn(const GemmArgs& a, int num_sms) {
   const char* env = getenv("GSTVD_GEMM_2CTA");
-  if (env == nullptr || atoi(env) == 0) return 0;
+  const int forced = env ? atoi(env) : 1;
+  if (forced == 0) return 0;
   const int esz = a.out_f32 ? 4 : 2;
   if (a.M < 8 * BM || a.N < 128 || a.K % 8 != 0 || (reinterpret_cast<uintptr_t>(a.C) & 15) != 0 || getenv("GSTVD_GEMM_NO_TMA_STORE") != nullptr)
     return 0;
+  if (a.fold_stats != nullptr || a.res != nullptr || a.stats_out != nullptr) return 0;   // deferred-LayerNorm epilogue: gemm_tc.cu only
   if (a.hm_D != 0) {
-    // head-major (cross-K/V prefill) output: its own switch until the plain mode has been validated
-    const char* hm_env = getenv("GSTVD_GEMM_2CTA_HM");
-    if (hm_env == nullptr || atoi(hm_env) == 0 || a.out_f32 || a.hm_D % 32 != 0 || a.M != a.hm_B * a.hm_L || a.N % (a.hm_D * a.hm_G) != 0 ||
-        getenv("GSTVD_GEMM_NO_TMA_HM") != nullptr)
+    if (a.out_f32 || a.hm_D % 32 != 0 || a.M != a.hm_B * a.hm_L || a.N % (a.hm_D * a.hm_G) != 0 || getenv("GSTVD_GEMM_NO_TMA_HM") != nullptr)
       return 0;
   } else if ((a.ldc * esz) % 16 != 0) {
     return 0;
   }
-  const int forced = atoi(env);
+  (void)num_sms;
   if (forced == 128 || forced == 256) return forced;
-  // the width that fills the 74 pairs best (a 128-column pair tile runs the tensor pipe at ~0.85 of the 256-column one)
-  const int cand[2] = {256, 128};
-  const double tile_eff[2] = {1.0, 0.85};
-  const int pairs = num_sms / 2;
-  const int64_t tm = (a.M + 2 * BM - 1) / (2 * BM);
-  double best = -1.0; int bn = 256;
-  for (int i = 0; i < 2; ++i) {
-    const int64_t tiles = tm * ((a.N + cand[i] - 1) / cand[i]);
-    const int64_t waves = (tiles + pairs - 1) / pairs;
-    const double used = (double)a.N / ((double)((a.N + cand[i] - 1) / cand[i]) * cand[i]);
-    const double eff = (double)tiles / (double)(waves * pairs) * tile_eff[i] * used;
-    if (eff > best + 1e-9) { best = eff; bn = cand[i]; }
-  }
-  return bn;
+  if (a.M >= 12288) return 256;
+  if (a.M >= 8192 && (a.N >= 2304 || a.K >= 2048)) return 256;
+  return 0;
 }
 
 }  // namespace

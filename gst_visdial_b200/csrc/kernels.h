@@ -73,18 +73,9 @@ constexpr float kLnEpsDeferred = 1e-12f;
 // SIMT GEMM: dtype kF32 (all fp32) or kBF16 (bf16 operands, fp32 accumulate; debugging aid)
 int launch_gemm_simt(const GemmArgs& a, int dtype, cudaStream_t stream);
 // tcgen05 / TMEM / TMA GEMM, bf16 operands, fp32 accumulate.
-// shared_sm: skinny (M <= 512) problems use the 6-warp / ~100 KB configuration of which two CTAs fit one SM
-int launch_gemm_tc(const GemmArgs& a, int num_sms, cudaStream_t stream, bool shared_sm = false);
+// Skinny (M <= 512) problems use the 6-warp / ~100 KB configuration of which two CTAs fit one SM.
+int launch_gemm_tc(const GemmArgs& a, int num_sms, cudaStream_t stream);
 void gemm_tc_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes
-// Fused Y = LN(A W^T + bias + res) for N = 768 (decode-step o / cross-o / FFN2 projections): one thread-block cluster per 64-row
-// block exchanges the row statistics through distributed shared memory.  `cluster` = 16 (48-column tiles) or 8 (96-column tiles).
-// EXPERIMENTAL: off unless env GSTVD_FUSE_LN is set (gemm_ln_mode() returns the cluster size, 0 = off).
-int gemm_ln_mode();
-bool gemm_ln_tc_supported(int M, int N, int K, const void* A, int64_t lda, const void* W, int64_t ldw, const void* res, int64_t ldr,
-                          const void* Y, int64_t ldy);
-int launch_gemm_ln_tc(const GemmArgs& a, const void* res, int64_t ldr, const float* gamma, const float* beta, float eps, void* Y,
-                      int64_t ldy, int cluster, cudaStream_t stream);
-
 struct AttnArgs {
   const void* q = nullptr; int64_t q_bs = 0, q_hs = 0, q_rs = 0;   // element strides: batch, head, row
   const void* k = nullptr; int64_t k_bs = 0, k_hs = 0, k_rs = 0;

@@ -235,18 +235,6 @@ class Engine:
                                                         _ptr(r), _ptr(g), _ptr(b), _ptr(y), self._stream()))
         return y
 
-    def op_linear_add_layernorm(self, a, w, bias, residual, gamma, beta, cluster=16):
-        """LN(a w^T + bias + residual) through the fused cluster kernel (bf16 operands); w is [768, K]."""
-        a, w = self._dev(a, torch.float32), self._dev(w, torch.float32)
-        b, r = self._dev(bias, torch.float32), self._dev(residual, torch.float32)
-        g, be = self._dev(gamma, torch.float32), self._dev(beta, torch.float32)
-        M, K = a.shape
-        assert w.shape == (768, K), w.shape
-        y = torch.empty(M, 768, dtype=torch.float32, device=a.device)
-        check(self.ctx, self.lib.gstvd_op_linear_add_layernorm(self.ctx, M, K, _ptr(a), _ptr(w), _ptr(b), _ptr(r), _ptr(g), _ptr(be),
-                                                               int(cluster), _ptr(y), self._stream()))
-        return y
-
     def op_deferred_ln_chain(self, a1, w1, b1, res0, gamma1, beta1, w2, b2, gamma2, beta2, want_x1=False):
         """LN2(LN1(x1) w2^T + b2 + LN1(x1)) with x1 = a1 w1^T + b1 + res0, through the decode step's deferred-LayerNorm GEMM
         epilogues (no LayerNorm kernel between the two GEMMs).  bf16 contexts; fp32 tensors in and out."""

@@ -78,8 +78,6 @@ typedef struct {
 #define GSTVD_FLAG_DEBUG_SIMT_GEMM 2 /* debugging aid: route bf16 GEMMs through the SIMT kernel */
 #define GSTVD_FLAG_NO_PDL 8          /* decode-step kernels without programmatic dependent launch */
 #define GSTVD_FLAG_GENERIC_ATTENTION 4 /* debugging aid: route bf16 attention through the generic SIMT kernel */
-#define GSTVD_FLAG_SHARED_SM_GEMM 16  /* accepted for compatibility, no effect: the decode-step GEMMs always run the 64-row configuration
-                                        * of which two CTAs share an SM, so contexts on separate streams overlap their decode steps */
 
 typedef struct {
   int32_t mode;               /* gstvd_select_mode */
@@ -188,13 +186,6 @@ int gstvd_op_linear(gstvd_ctx* ctx, int dtype, int M, int N, int K, const float*
 /* y = LayerNorm(x + residual) with eps 1e-12 inside the sqrt (models/vilbert_dialog.py:283-296). residual may be NULL */
 int gstvd_op_add_layernorm(gstvd_ctx* ctx, int dtype, int rows, int width, const float* x, const float* residual,
                            const float* gamma, const float* beta, float* y, void* stream);
-/* y = LayerNorm(a[M,K] * w[768,K]^T + bias + residual) in ONE launch (bf16 operands, fp32 accumulate and statistics): the
- * experimental fused form of the decoder's dense -> LayerNorm(x + input) pairs (HF BertSelfOutput / BertOutput called from
- * models/visual_dialog_decoder.py:300-311).  N is fixed at 768, K % 256 == 0; cluster = 16 or 8 CTAs per 64-row block.
- * All buffers fp32 on the device (rounded to bf16 inside, like gstvd_op_linear). */
-int gstvd_op_linear_add_layernorm(gstvd_ctx* ctx, int M, int K, const float* a, const float* w, const float* bias,
-                                  const float* residual, const float* gamma, const float* beta, int cluster, float* y,
-                                  void* stream);
 /* softmax(q k^T / sqrt(D) + (1-mask)*neg [+ causal]) v ; q [B,Lq,H*D], k/v [B,Lk,H*D], mask [B,Lk] or NULL */
 int gstvd_op_attention(gstvd_ctx* ctx, int dtype, int B, int H, int Lq, int Lk, int D, const float* q, const float* k,
                        const float* v, const float* mask, float neg, int causal, float* out, void* stream);

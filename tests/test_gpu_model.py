@@ -637,3 +637,31 @@ def test_evaluate_gen_cli_synthetic(tmp_path):
     assert len(out) == 6 and sorted(out[0]["ranks"]) == list(range(1, 8)) and {d["round_id"] for d in out} == {1, 2}
     m = json.loads(r.stdout.strip().splitlines()[-1])
     assert 0.0 <= m["mrr"] <= 1.0 and 1.0 <= m["mean"] <= 7.0
+
+
+def test_pair_gemm_encoder_prefill_match_single(full_cfgs, full_sd):
+    """Whole encoder, cross-K/V prefill (head-major TMA-store epilogue) and the decode that reads the cache with the CTA-pair GEMM
+    forced on every eligible problem against the single-CTA kernel: outputs within bf16 noise, token ids identical."""
+    from gst_visdial_b200.engine import Engine
+    enc_cfg, dec_cfg = full_cfgs
+    B = 8
+    e = Engine(enc_cfg, dec_cfg, dtype="bf16", max_batch=B, max_beams=5)
+    e.load_state_dict(full_sd)
+    try:
+        b = history_batch(enc_cfg, 0, B)
+        outs = []
+        for flag in ("0", "256"):
+            os.environ["GSTVD_GEMM_2CTA"] = flag
+            try:
+                o = e.encode(b["enc_input_ids"], b["enc_image_feat"], b["enc_image_loc"], b["enc_segments"], b["enc_att_mask"],
+                             b["enc_image_mask"], want_t=True, want_v=True, want_fused=True)
+                e.prefill_cross(B, o["Le"])
+            finally:
+                os.environ.pop("GSTVD_GEMM_2CTA", None)
+            outs.append((o["seq_t"].cpu(), o["seq_v"].cpu(), o["fused"].cpu(), e.generate(B, num_beams=1, top_k=1).cpu(),
+                         e.generate(B, num_beams=5).cpu()))
+        for x0, x1 in zip(outs[0][:3], outs[1][:3]):
+            assert torch.isfinite(x1).all() and rel_rms(x1, x0) < 1e-3, rel_rms(x1, x0)
+        assert torch.equal(outs[0][3], outs[1][3]) and torch.equal(outs[0][4], outs[1][4])
+    finally:
+        e.close()

@@ -65,5 +65,4 @@ for _ in range(5):
 g1.record()
 torch.cuda.synchronize()
 w = torch.arange(1, ids.numel() + 1, device=ids.device, dtype=torch.int64).view_as(ids)
-print(f"generate only: {g0.elapsed_time(g1) / 5:.3f} ms per call; ids checksum {int((ids * w).sum())}; "
-      f"FUSE_LN={os.environ.get('GSTVD_FUSE_LN', '0')}")
+print(f"generate only: {g0.elapsed_time(g1) / 5:.3f} ms per call; ids checksum {int((ids * w).sum())}")
