@@ -79,3 +79,22 @@ def test_jsonl_writer_and_reference_json(tmp_path):
     n = O.jsonl_to_reference_json(p, str(tmp_path / "out.json"))
     data = json.load(open(tmp_path / "out.json"))
     assert n == 4 and data[0] == recs[0] and data[3] == txt[1]
+
+
+def test_reader_matches_reference_reader_goldens(golden_dir):
+    """the product reader (gst_visdial_b200/io/features.py) and its oracle (oracle/io_reader.py) against
+    tests/golden/io_records.npz - outputs of the REFERENCE'S OWN ImageFeaturesH5Reader + encode_image_input
+    (utils/image_features_reader.py:58-141, utils/data_utils.py:73-117) run on the same seeded records by oracle/gen_golden_io.py."""
+    import hashlib
+    from oracle.gen_golden_io import CASES, make_reference_record
+    g = dict(np.load(os.path.join(golden_dir, "io_records.npz")))
+    for i in range(len(CASES)):
+        rec = make_reference_record(i)
+        for reader, padder in ((F.decode_reference_record, F.pad_regions), (RO.read_record, RO.encode_image_input)):
+            f, nb, loc = reader(rec)
+            assert nb == int(g[f"c{i}_num_boxes"]) == CASES[i][0] + 1
+            assert np.array_equal(f[0], g[f"c{i}_global_row"]) and np.array_equal(np.asarray(loc), g[f"c{i}_loc"])
+            pf, ps, pm = padder(f, nb, loc)
+            assert np.array_equal(ps, g[f"c{i}_pad_loc"]) and np.array_equal(pm, g[f"c{i}_pad_mask"])
+            sha = np.frombuffer(hashlib.sha256(np.ascontiguousarray(pf).tobytes()).digest(), dtype=np.uint8)
+            assert np.array_equal(sha, g[f"c{i}_pad_feat_sha256"]), f"case {i}: padded feature block differs from the reference reader's"
