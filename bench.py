@@ -422,9 +422,16 @@ def decode_step_roofline(a, sl, dev, peaks, peak_src):
     total = w_bytes + cross_bytes + self_bytes
     peak = float(peaks.get("hbm_gbs", 6650.0))
     ach = total / (ms_step * 1e-3) / 1e9
+    traffic = None                                  # dram read + write of one whole decode step from the committed ncu capture
+    tp = os.path.join(ROOT, "profiles", "decode_step_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_step")
+        except Exception:
+            traffic = None
     return {"kernel": f"decode step ({geo['kernels_per_step']} kernels: 12 x [qkv GEMM, self-attention, o GEMM, cross-q GEMM, cross-attention, "
                       f"cross-o GEMM, FFN1, FFN2] + LM head + selection, CUDA-graph replay)",
-            "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
             "peak_source": peak_src + ", hbm_gbs",
             "ms_per_decode_step": ms_step, "rows": B * K,
             "algorithmic_bytes_per_step": total,

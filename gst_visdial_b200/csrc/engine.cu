@@ -655,8 +655,10 @@ void decode_step(gstvd_ctx* c, const DecodeGeom& g, const gstvd_gen_params& gp, 
   float* sv = (float*)c->sel_val.p; int32_t* si = (int32_t*)c->sel_idx.p;
   if (gp.mode == GSTVD_SELECT_BEAM) {
     const int nsel = 2 * g.K;
-    c->launches += launch_row_select(M, c->V, (const float*)c->logits.p, c->Vpad, 0, (const float*)c->beam_scores.p, 1.f, nullptr,
-                                     nullptr, 0, nsel, sv, si, nullptr, s);
+    // bf16: log-sum-exp terms in fp32 (mode 2); the fp32 parity path keeps the fp64 terms of the bit-exact contract (mode 0)
+    static const bool exact_lse = getenv("GSTVD_EXACT_LSE") != nullptr;
+    c->launches += launch_row_select(M, c->V, (const float*)c->logits.p, c->Vpad, (c->dtype == kBF16 && !exact_lse) ? 2 : 0,
+                                     (const float*)c->beam_scores.p, 1.f, nullptr, nullptr, 0, nsel, sv, si, nullptr, s);
     BeamBuffers bb = beam_buffers(c);
     c->launches += launch_beam_step(bb, g.B, g.K, g.T, c->V, nsel, sv, si, 102, nullptr, nullptr, nullptr, s);
     if (use_anc) c->launches += launch_anc_update(g, bb.beam_idx, d_step, (uint8_t*)c->anc.p, s);

@@ -157,7 +157,7 @@ int launch_reorder_cache(int dtype, const DecodeGeom& g, void* self_cache, const
 // ---- token selection -------------------------------------------------------------------------------------
 constexpr int kSelMax = 16;   // per-row candidates kept (>= 2*max_beams, >= max top_k)
 // Per row: logZ (fp64 accumulate) and the top `nsel` entries of  score_j by (score desc, index asc), where
-//   mode 0 (beam):   score_j = fp32(fp32(x_j - logZ) + row_bias[row])
+//   mode 0 (beam):   score_j = fp32(fp32(x_j - logZ) + row_bias[row])   (mode 2: the same with the exp terms of logZ in fp32)
 //   mode 1 (sample): score_j = x_j / temperature, banned tokens = -inf
 // logits [rows, ldl] fp32.  ban_tokens [rows, ban_stride] / ban_count [rows] may be null.
 int launch_row_select(int rows, int V, const float* logits, int64_t ldl, int mode, const float* row_bias, float temperature,

@@ -182,11 +182,12 @@ __device__ __forceinline__ double exp_nonpos(double d, const double* __restrict_
 }
 
 __global__ void __cluster_dims__(kRsChunks, 1, 1) __launch_bounds__(kRsThreads, 4)
-row_select_cluster_kernel(int V, const float* __restrict__ logits, int64_t ldl, int mode, const float* __restrict__ row_bias,
+row_select_cluster_kernel(int V, const float* __restrict__ logits, int64_t ldl, int mode_in, const float* __restrict__ row_bias,
                           float temperature, const int32_t* __restrict__ ban_tokens, const int32_t* __restrict__ ban_count,
                           int ban_stride, int nsel, float* __restrict__ sel_val, int32_t* __restrict__ sel_idx, float* __restrict__ logz) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
+  int mode = mode_in;
   __shared__ float s_f[kRsWarps];
   __shared__ double s_d[kRsWarps];
   __shared__ int s_i[kRsWarps];
@@ -217,6 +218,10 @@ row_select_cluster_kernel(int V, const float* __restrict__ logits, int64_t ldl, 
   if (tid == 0) s_cnt = 0;
   if (tid < 32) s_exp2[tid] = kExp2Table[tid];
   float lz = 0.f;
+  // mode 2 = mode 0 (beam scores) with the log-sum-exp terms in fp32 (ex2.approx): the bf16 decode step, whose logits carry
+  // ~1e-2 of rounding noise anyway; mode 0 keeps the fp64 terms of the bit-exact contract (oracle/beam.py, fp32 path, op tests)
+  const bool fast_lse = mode == 2;
+  if (fast_lse) mode = 0;
   const bool need_lz = (mode == 0 || logz != nullptr);
   if (need_lz) {
     float m = -INFINITY;
@@ -229,10 +234,25 @@ row_select_cluster_kernel(int V, const float* __restrict__ logits, int64_t ldl, 
     m = warp_max(m);
     double acc = 0.0;
     if (m > -INFINITY) {
-      const double md = (double)m;
-      // no bounds test per slot: slots past the vocabulary hold -inf and add exp(-700) ~ 1e-304, i.e. nothing
+      if (fast_lse) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;            // four independent chains; exp2(-inf) = 0 for the slots past the vocabulary
+        const float ms = m * 1.44269504088896340736f;
 #pragma unroll
-      for (int s = 0; s < kRsSlots; ++s) acc += exp_nonpos((double)v[s] - md, s_exp2);
+        for (int s = 0; s < kRsSlots; s += 4) {
+          float e0, e1, e2, e3;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(v[s], 1.44269504088896340736f, -ms)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(v[s + 1], 1.44269504088896340736f, -ms)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmaf(v[s + 2], 1.44269504088896340736f, -ms)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(fmaf(v[s + 3], 1.44269504088896340736f, -ms)));
+          a0 += e0; a1 += e1; a2 += e2; a3 += e3;
+        }
+        acc = (double)((a0 + a1) + (a2 + a3));
+      } else {
+        const double md = (double)m;
+        // no bounds test per slot: slots past the vocabulary hold -inf and add exp(-700) ~ 1e-304, i.e. nothing
+#pragma unroll
+        for (int s = 0; s < kRsSlots; ++s) acc += exp_nonpos((double)v[s] - md, s_exp2);
+      }
     }
     acc = warp_sum(acc);
     if (lane == 0) s_d[warp] = acc;
@@ -733,7 +753,7 @@ int launch_row_select(int rows, int V, const float* logits, int64_t ldl, int mod
   if (nsel > kSelMax || nsel < 1) throw std::runtime_error("row_select: nsel out of range");
   static const bool v1 = getenv("GSTVD_ROW_SELECT_V1") != nullptr;      // A/B aid: the single-CTA-per-row kernel
   if (v1)
-    launch_k(row_select_kernel, dim3(rows), dim3(kSelThreads), 0, stream, V, logits, ldl, mode, row_bias, temperature, ban_tokens, ban_count,
+    launch_k(row_select_kernel, dim3(rows), dim3(kSelThreads), 0, stream, V, logits, ldl, mode == 2 ? 0 : mode, row_bias, temperature, ban_tokens, ban_count,
              ban_stride, nsel, sel_val, sel_idx, logz);
   else
     launch_k(row_select_cluster_kernel, dim3(rows * kRsChunks), dim3(kRsThreads), 0, stream, V, logits, ldl, mode, row_bias, temperature,

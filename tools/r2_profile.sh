@@ -1,6 +1,7 @@
 #!/bin/bash
-# ncu evidence for the round-2 default kernels (one gpurun call, one GPU).  Output: gpurun_out/r2p_*.  Numbers printed under a
-# profiler are never bench values; per-launch times are serialised (no PDL overlap) - compare shares and utilisation.
+# ncu evidence for the round-2 default kernels (one gpurun call, one GPU).  Output: gpurun_out/r2p_* (text summaries; the .ncu-rep
+# files are deleted except the small source-annotated one - gpurun copies back at most 64 MiB).  Numbers printed under a profiler
+# are never bench values; per-launch times are serialised (no PDL overlap) - compare shares and utilisation.
 set -u
 mkdir -p gpurun_out
 R="python tools/profile_round.py --hist 150"
@@ -8,20 +9,17 @@ R="python tools/profile_round.py --hist 150"
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --cache-control none --csv \
     --log-file gpurun_out/r2p_launches_warm.csv $R > gpurun_out/r2p_ncu0.log 2>&1
 python tools/agg_launches.py gpurun_out/r2p_launches_warm.csv > gpurun_out/r2p_launches_warm.txt
-# 2. --set full captures
-cap() {  # name regex skip count
-  timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k "regex:$2" -s "$3" -c "$4" -f \
-      -o "gpurun_out/r2p_$1" $R > "gpurun_out/r2p_$1.log" 2>&1
+python tools/agg_launches.py gpurun_out/r2p_launches_warm.csv 340 | tail -340 > gpurun_out/r2p_launch_sequence_head.txt
+# 2. --set full: one whole decode step (103 kernels from the CUDA graph), the encoder's first 70 launches, no source import
+cap() {  # name skip count
+  timeout 900 ncu --profile-from-start off --set full --clock-control none -s "$2" -c "$3" -f -o "gpurun_out/r2p_$1" $R > "gpurun_out/r2p_$1.log" 2>&1
   python tools/ncu_summary.py "gpurun_out/r2p_$1.ncu-rep" > "gpurun_out/r2p_$1_summary.txt" 2>&1
+  rm -f "gpurun_out/r2p_$1.ncu-rep"
 }
-cap enc_gemm_single 'gemm_tc_kernel' 4 6
-cap enc_gemm_pair 'gemm_tc2_kernel' 8 4
-cap decode_step_gemms 'gemm_tc_kernel' 400 74
-cap self_attn 'dec_self_attn_v2' 30 1
-cap anc_update 'anc_update' 5 1
-cap cross_tma 'dec_cross_tma2' 30 1
-cap row_select 'row_select_cluster' 5 1
-cap ln_apply 'ln_apply_stats' 5 1
-cap enc_attention 'attention_mma' 3 3
-cap enc_ln 'add_layernorm_stream' 3 1
-ls -la gpurun_out/r2p_* | head -40
+cap decode_step 533 103
+cap encoder_head 0 70
+# 3. the decode GEMM with the deferred-LayerNorm epilogue, source-annotated (kept)
+timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k "regex:gemm_tc_kernel" -s 300 -c 3 -f \
+    -o gpurun_out/r2p_decode_gemm_src $R > gpurun_out/r2p_decode_gemm_src.log 2>&1
+python tools/ncu_summary.py gpurun_out/r2p_decode_gemm_src.ncu-rep > gpurun_out/r2p_decode_gemm_src_summary.txt 2>&1
+du -sh gpurun_out; ls gpurun_out | head -30
