@@ -49,7 +49,7 @@ GF_ENCODER, GF_PREFILL, GF_DECODE_ROW, GF_SCORE18 = 76.66, 8.30, 4.61, 12.91
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="gen_teacher", choices=WORKLOADS)
