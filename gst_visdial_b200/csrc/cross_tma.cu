@@ -16,6 +16,7 @@
 // softmax over all fetched keys (scores in shared memory) in the log2 domain.
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
 
@@ -236,8 +237,14 @@ struct X2Cfg {
 template <int kX2Warps, int kStages, int kX2Groups>
 __global__ void __launch_bounds__(kX2Warps * 32, kStages == 1 ? 2 : 1)
 dec_cross_tma2_kernel(const __grid_constant__ CUtensorMap tm, DecodeGeom g, int layer, const bf16* __restrict__ q,
-                      const float* __restrict__ enc_mask, const int* __restrict__ cross_len, bf16* __restrict__ out) {
+                      const float* __restrict__ enc_mask, const int* __restrict__ cross_len, bf16* __restrict__ out,
+                      unsigned long long* __restrict__ stamps_all) {
   extern __shared__ uint8_t xt_raw[];
+  // measurement aid (env GSTVD_CROSS_TIMES): 16 globaltimer stamps per CTA - start, dependency resolved, then per item
+  // K arrived / scores done / V arrived / item stored
+  unsigned long long* stamps = (stamps_all != nullptr && threadIdx.x == 0) ? stamps_all + (size_t)blockIdx.x * 16 : nullptr;
+  auto stamp = [&](int i) { if (stamps != nullptr && i < 16) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); stamps[i] = t; } };
+  stamp(0);
   const uint32_t raw = smem_u32(xt_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;             // swizzled boxes need 1024-byte alignment
   uint8_t* gen = xt_raw + (base - raw);
@@ -321,6 +328,7 @@ dec_cross_tma2_kernel(const __grid_constant__ CUtensorMap tm, DecodeGeom g, int 
   load_mask(first / g.heads);
   store_mask(madd);
   pdl_wait();                                               // the query projection of this step is complete
+  stamp(1);
   load_q(first);
 
   const float sc = kLog2e / 8.0f;                           // scores / sqrt(64), log2 domain
@@ -344,6 +352,7 @@ dec_cross_tma2_kernel(const __grid_constant__ CUtensorMap tm, DecodeGeom g, int 
     if (next < items) load_mask(next / g.heads);
     __syncthreads();                                        // (1) mask row visible; the previous item's shared results have been read
     mbar_wait(bar_k(s), phase);
+    stamp(2 + 4 * it);
     // ---- scores of this warp's key groups: s[gi][0..1] keys 16G + p4*2 + {0,1}, s[gi][2..3] the same + 8; row = beam ----
     float sv[kX2Groups][4];
     float mloc = -INFINITY;
@@ -373,6 +382,7 @@ dec_cross_tma2_kernel(const __grid_constant__ CUtensorMap tm, DecodeGeom g, int 
     mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 2));
     if (p4 == 0) wmax[warp * 8 + beam] = mloc;
     __syncthreads();                                        // (2) per-warp maxima visible
+    stamp(3 + 4 * it);
     if (warp == 0 && ahead < items) issue(ahead, 0, s, nk_ahead);   // every warp is past its scores: the K buffer is free
     if (next < items) {
       load_q(next);                                         // in flight during the rest of this item
@@ -397,6 +407,7 @@ dec_cross_tma2_kernel(const __grid_constant__ CUtensorMap tm, DecodeGeom g, int 
     sloc += __shfl_xor_sync(0xffffffffu, sloc, 2);
     if (p4 == 0) wsum[warp * 8 + beam] = sloc;
     mbar_wait(bar_v(s), phase);
+    stamp(4 + 4 * it);
     // ---- context: O[beam][d] += P[beam][keys of the group] V[keys][d] ----
     float o[8][4];
 #pragma unroll
@@ -432,6 +443,7 @@ dec_cross_tma2_kernel(const __grid_constant__ CUtensorMap tm, DecodeGeom g, int 
       }
       out[((int64_t)(b * g.K + k)) * g.H + h * 64 + d] = __float2bfloat16_rn(v / t);
     }
+    stamp(5 + 4 * it);
     nk0 = nk1; nk1 = nk2; nk2 = nk3;
   }
 }
@@ -450,6 +462,25 @@ __global__ void cross_len_kernel(int B, int Le, const float* __restrict__ mask, 
 }
 
 }  // namespace
+
+unsigned long long* g_cross_stamps = nullptr;
+
+// Prints the stamps of the most recent dec_cross_tma2 launch (after a device synchronisation); measurement aid.
+void dec_cross_print_times() {
+  if (g_cross_stamps == nullptr) return;
+  cudaDeviceSynchronize();
+  static unsigned long long h[1024 * 16];
+  cudaMemcpy(h, g_cross_stamps, sizeof h, cudaMemcpyDeviceToHost);
+  unsigned long long t0 = ~0ull; int ctas = 0;
+  for (int i = 0; i < 1024; ++i) if (h[i * 16]) { if (h[i * 16] < t0) t0 = h[i * 16]; ++ctas; }
+  const char* names[14] = {"start", "dep", "i0 K", "i0 scores", "i0 V", "i0 done", "i1 K", "i1 scores", "i1 V", "i1 done", "i2 K", "i2 scores", "i2 V", "i2 done"};
+  fprintf(stderr, "[cross times, %d CTAs] ns since the first CTA started, mean / max over the CTAs that reached the stamp (count):\n", ctas);
+  for (int j = 0; j < 14; ++j) {
+    double sum = 0, mx = 0; int n = 0;
+    for (int i = 0; i < 1024; ++i) if (h[i * 16] && h[i * 16 + j] >= h[i * 16]) { const double v = (double)(h[i * 16 + j] - t0); sum += v; if (v > mx) mx = v; ++n; }
+    if (n) fprintf(stderr, "  %-10s %8.0f / %8.0f  (%d)\n", names[j], sum / n, mx, n);
+  }
+}
 
 bool dec_cross_tma_supported(int dtype, const DecodeGeom& g) {
   static const bool off = getenv("GSTVD_CROSS_NO_TMA") != nullptr;
@@ -475,15 +506,18 @@ int launch_dec_cross_tma(const DecodeGeom& g, int layer, const void* q, const vo
   const int items = g.B * g.heads;
   const int slots = variant == 3 ? num_sms : 2 * num_sms;
   const int grid = items < slots ? items : slots;
+  static unsigned long long* d_stamps = nullptr;          // measurement aid: GSTVD_CROSS_TIMES=1, read back by dec_cross_print_times()
+  static const bool want_times = getenv("GSTVD_CROSS_TIMES") != nullptr;
+  if (want_times && d_stamps == nullptr) { cudaMalloc(&d_stamps, 1024 * 16 * 8); cudaMemset(d_stamps, 0, 1024 * 16 * 8); g_cross_stamps = d_stamps; }
   if (variant == 1)
     launch_k(dec_cross_tma_kernel, dim3(grid), dim3(kXtThreads), (size_t)kXtSmem, stream, *tm, g, layer, (const bf16*)q, enc_mask, cross_len,
              (bf16*)out);
   else if (variant == 3)
     launch_k(dec_cross_tma2_kernel<16, 2, 2>, dim3(grid), dim3(Cfg3::kThreads), (size_t)Cfg3::kSmem, stream, *tm, g, layer, (const bf16*)q,
-             enc_mask, cross_len, (bf16*)out);
+             enc_mask, cross_len, (bf16*)out, d_stamps);
   else
     launch_k(dec_cross_tma2_kernel<8, 1, 3>, dim3(grid), dim3(Cfg2::kThreads), (size_t)Cfg2::kSmem, stream, *tm, g, layer, (const bf16*)q,
-             enc_mask, cross_len, (bf16*)out);
+             enc_mask, cross_len, (bf16*)out, d_stamps);
   return 1;
 }
 

@@ -903,6 +903,7 @@ int gstvd_create(const gstvd_config* cfg, int device, gstvd_ctx** out) {
 
 void gstvd_destroy(gstvd_ctx* c) {
   if (!c) return;
+  if (getenv("GSTVD_CROSS_TIMES") != nullptr) dec_cross_print_times();
   int prev = -1; cudaGetDevice(&prev);
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();

@@ -148,6 +148,7 @@ bool dec_cross_tma_supported(int dtype, const DecodeGeom& g);
 int launch_dec_cross_tma(const DecodeGeom& g, int layer, const void* q, const void* cross_cache, const float* enc_mask,
                          const int* cross_len, void* out, int num_sms, cudaStream_t stream);
 int launch_cross_len(int B, int Le, const float* mask, int* out, cudaStream_t stream);
+void dec_cross_print_times();   // measurement aid (env GSTVD_CROSS_TIMES=1): per-CTA phase stamps of the last cross-attention launch
 // cached CUtensorMap (returned as an opaque pointer) over [groups][L][D] bf16 rows, box = D x box_rows (gemm_tc.cu)
 const void* tma_map_rows3(const void* ptr, int D, int L, int64_t groups, int box_rows);
 // in-place beam gather of the self cache over positions [0, len) ; len = *d_len if d_len else len_host

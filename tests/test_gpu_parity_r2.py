@@ -247,3 +247,33 @@ def test_sampler_is_keyed_by_global_row(tiny_cfgs, tiny_sd):
     other = torch.stack([e.op_sample(logits, step=s, seed=100, **kw).cpu() for s in range(12)], 1)
     assert not torch.equal(other, whole)
     e.close()
+
+
+def test_config4_config5_helpers_are_exact_under_trimming_and_chunking(tiny_cfgs, tiny_sd):
+    """bench.py's config 4 / 5 paths: answer_perplexity with the host-side history bound == without it (padded positions are
+    never read), and nsp_rank_items (image features expanded on the device per chunk, trimmed) == nsp_rank on the fully expanded
+    rows - bit for bit, in bf16."""
+    from gst_visdial_b200 import ranking as RK, synthetic as S, weights as W
+    from gst_visdial_b200.models.visual_dialog_encoder import VisualDialogEncoder
+    from test_gpu_model import _build_model, _params
+    enc_cfg, dec_cfg = tiny_cfgs
+    vs, vf = enc_cfg.vocab_size, enc_cfg.v_feature_size
+    model, _ = _build_model(W.TINY_ENC_CONFIG, W.TINY_DEC_CONFIG, tiny_sd, "bf16")
+    b = S.synthetic_history_batch(0, 6, vocab_size=vs, v_feature_size=vf, rounds=[0, 1, 2, 3, 4, 5])
+    ans = torch.stack([S.synthetic_utterance(i, 99, vs) for i in range(6)])
+    dev = {k: v.cuda() for k, v in b.items() if k != "hist_len_bound"}
+    p_full = RK.answer_perplexity(model, dev, ans.cuda(), device="cuda:0")
+    p_trim = RK.answer_perplexity(model, dev, ans.cuda(), device="cuda:0", trim_history=True, hist_len_bound=int(b["hist_len_bound"][0]))
+    assert torch.isfinite(p_full).all() and torch.equal(p_full, p_trim)
+    params = _params(W.TINY_ENC_CONFIG, W.TINY_DEC_CONFIG, "bf16", model="enc_only_a", mode="vd_eval_val", engine_max_batch=16)
+    enc = VisualDialogEncoder(params)
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in tiny_sd.items() if k.startswith("encoder.")})
+    enc.to("cuda:0").eval()
+    items = S.synthetic_candidate_batch(0, 3, 5, vocab_size=vs, v_feature_size=vf)
+    got = RK.nsp_rank_items(enc, items, chunk=4, device="cuda:0", trim_history=True)           # chunks straddle items
+    flat = {"tokens": items["tokens"].reshape(15, -1), "segments": items["segments"].reshape(15, -1), "mask": items["mask"].reshape(15, -1),
+            "image_feat": items["image_feat"].repeat_interleave(5, 0), "image_loc": items["image_loc"].repeat_interleave(5, 0),
+            "image_mask": items["image_mask"].repeat_interleave(5, 0)}
+    want = RK.nsp_rank(enc, flat, device="cuda:0").reshape(3, 5)
+    assert got.shape == (3, 5) and torch.equal(got, want)
+    assert ((got > 0) & (got < 1)).all()

@@ -162,3 +162,40 @@ def test_jsonl_writer_raises_instead_of_deadlocking(tmp_path):
         w.close()
     except Exception:                                  # noqa: BLE001 - close re-raises the writer's error
         pass
+
+
+def test_synthetic_history_and_candidate_batches():
+    """Input builders of bench.py's config 4 / 5 workloads: shapes, the reference's segment / mask conventions and the host-side
+    length bound the encoder trimming relies on (no token at or past it)."""
+    from gst_visdial_b200 import synthetic as S
+    b = S.synthetic_history_batch(5, 6, rounds=[0, 1, 3, 9, 30, 2])
+    ids, seg = b["enc_input_ids"], b["enc_segments"]
+    assert ids.shape == (6, 256) and b["enc_image_feat"].shape == (6, 37, 2048)
+    bound = int(b["hist_len_bound"][0])
+    assert bound <= 256 and not (ids[:, bound:] != 0).any() and (ids[:, bound - 1] != 0).any()
+    assert torch.equal(b["enc_att_mask"], (ids != 0).float())
+    assert int((ids[0] != 0).sum()) < int((ids[3] != 0).sum())           # more rounds, longer history
+    assert not (ids[:, 1:] == 101).any() and (ids[:, 0] == 101).all()
+    n0 = int((ids[1] != 0).sum())
+    cap = int(seg[1].sum().item())                                          # caption (segment 1) + one answer (segment 1), question segment 0
+    assert 0 < cap < n0
+    c = S.synthetic_candidate_batch(3, 4, 7)
+    tok, sg, mk = c["tokens"], c["segments"], c["mask"]
+    assert tok.shape == (4, 7, 256) and c["image_feat"].shape == (4, 37, 2048)
+    assert torch.equal(mk, (tok != 0).float())
+    cb = int(c["hist_len_bound"][0])
+    assert not (tok[..., cb:] != 0).any()
+    for i in range(4):
+        assert torch.equal(tok[i, 0, :20], tok[i, 1, :20])                  # the candidates of an item share its history ...
+        assert not torch.equal(tok[i, 0], tok[i, 1])                        # ... and differ in the appended answer
+        last = int((tok[i, 0] != 0).sum()) - 1
+        assert int(tok[i, 0, last]) == 102                                  # every utterance ends in [SEP]; the mask reaches the last one
+
+
+def test_history_trim_helper():
+    from gst_visdial_b200.ranking import _trim
+    ids = torch.zeros(3, 256, dtype=torch.int64); ids[:, :70] = 5
+    seg, att = torch.zeros_like(ids), (ids != 0).float()
+    a, b, c = _trim(ids, seg, att, 70)
+    assert a.shape == (3, 96) and b.shape == (3, 96) and c.shape == (3, 96) and a.is_contiguous()
+    assert _trim(ids, seg, att, None)[0] is ids and _trim(ids, seg, att, 250)[0] is ids and _trim(ids, None, None, 10)[0].shape == (3, 32)
