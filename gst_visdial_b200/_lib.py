@@ -68,6 +68,7 @@ SYMBOLS = [
     ("gstvd_encode", c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("gstvd_prefill_cross", c_int, [_P, c_int, c_int, _P, _P, _P]),
     ("gstvd_generate", c_int, [_P, c_int, POINTER(GstvdGenParams), _P, _P, c_int, _P, _P, _P]),
+    ("gstvd_round", c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, POINTER(GstvdGenParams), _P, _P, _P]),
     ("gstvd_score", c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     ("gstvd_score_options", c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     ("gstvd_reorder_cache", c_int, [_P, c_int, c_int, c_int, _P, _P]),

@@ -126,6 +126,13 @@ struct gstvd_ctx {
   struct GraphEntry { cudaGraphExec_t exec; int64_t kernels; uint64_t last_use; };   // kernels per replay, counted during capture
   std::map<GraphKey, GraphEntry> graphs;
   uint64_t graph_clock = 0;
+  // whole-round graphs (gstvd_round): encoder + cross-K/V prefill + every decode step of one forward call in ONE graph, keyed by shapes
+  struct RoundKey {
+    int B, Lt, Lv, K, mode, T, top_k, ngram, has_seg, has_att, has_imask; float temperature, top_p;
+    bool operator<(const RoundKey& o) const { return std::memcmp(this, &o, sizeof(RoundKey)) < 0; }
+  };
+  std::map<RoundKey, GraphEntry> round_graphs;
+  DevBuf r_ids, r_seg, r_att, r_feat, r_loc, r_imask, r_out_ids, r_out_scores;   // context-owned copies of a round's inputs / outputs
   DevBuf hist_ids_own, hist_seg_own;                  // int64 [B_max, Lt_max]: n-gram blocking history read by captured graphs
   // optional event profiling of the tcgen05 GEMM launches (bench.py roofline): one event pair per launch
   bool profiling = false; int prof_min_rows = 0;
@@ -326,6 +333,9 @@ void alloc_workspace(gstvd_ctx* c) {
     c->sel_val.alloc(R * kSelMax * 4); c->sel_idx.alloc(R * kSelMax * 4); c->logz.alloc(R * 4);
     c->ban_tokens.alloc(B * Lt * 4); c->ban_count.alloc(B * 4);
     c->hist_ids_own.alloc(B * Lt * 8); c->hist_seg_own.alloc(B * Lt * 8);
+    c->r_ids.alloc(B * Lt * 8); c->r_seg.alloc(B * Lt * 8); c->r_att.alloc(B * Lt * 4);
+    c->r_feat.alloc(B * Lv * (size_t)c->cfg.v_feature_size * 4); c->r_loc.alloc(B * Lv * 5 * 4); c->r_imask.alloc(B * Lv * 4);
+    c->r_out_ids.alloc(B * T * 8); c->r_out_scores.alloc(B * 4);
     c->prefix.alloc(B * (T + 1) * 4); c->seq.alloc(B * T * 4);
     c->beam_scores.alloc(B * K * 4); c->beam_tokens.alloc(2 * B * K * T * 4); c->cur_tokens.alloc(R * 4);
     c->beam_idx.alloc(B * K * 4); c->beam_done.alloc(B); c->hyp_score.alloc(B * (K + 1) * 8);
@@ -679,11 +689,10 @@ void decode_step(gstvd_ctx* c, const DecodeGeom& g, const gstvd_gen_params& gp, 
   c->launches += launch_step_advance((int*)c->d_step.p, s);
 }
 
-void do_generate(gstvd_ctx* c, int B, const gstvd_gen_params& gp, const int64_t* hist_ids, const int64_t* hist_seg, int Lh,
-                 int64_t* out_ids, float* out_scores, cudaStream_t s) {
+// Argument checks of a generate call; returns the beams per image.
+int check_generate(gstvd_ctx* c, const gstvd_gen_params& gp, const int64_t* hist_ids, const int64_t* hist_seg, int Lh, const int64_t* out_ids) {
   check_ready(c);
   if (c->dec_layers == 0) throw StateError("generate: encoder-only context");
-  if (c->cross_B != B) throw StateError(fmt("generate: cross K/V prefilled for %d images, asked for %d", c->cross_B, B));
   const int T = gp.max_new_tokens;
   if (T < 1 || T > c->T_max) throw InvalidArg("generate: max_new_tokens out of range");
   if (!out_ids) throw InvalidArg("generate: out_ids is NULL");
@@ -699,6 +708,20 @@ void do_generate(gstvd_ctx* c, int B, const gstvd_gen_params& gp, const int64_t*
   } else {
     throw InvalidArg("generate: unknown mode");
   }
+  return K;
+}
+
+void generate_finalize(gstvd_ctx* c, int B, int K, const gstvd_gen_params& gp, int64_t* out_ids, float* out_scores, cudaStream_t s) {
+  const int T = gp.max_new_tokens;
+  if (gp.mode == GSTVD_SELECT_BEAM) c->launches += launch_beam_finalize(beam_buffers(c), B, K, T, 102, out_ids, out_scores, s);
+  else c->launches += launch_sample_finalize(B, T, 102, (const int32_t*)c->seq.p, out_ids, s);
+}
+
+void do_generate(gstvd_ctx* c, int B, const gstvd_gen_params& gp, const int64_t* hist_ids, const int64_t* hist_seg, int Lh,
+                 int64_t* out_ids, float* out_scores, cudaStream_t s) {
+  const int K = check_generate(c, gp, hist_ids, hist_seg, Lh, out_ids);
+  if (c->cross_B != B) throw StateError(fmt("generate: cross K/V prefilled for %d images, asked for %d", c->cross_B, B));
+  const int T = gp.max_new_tokens;
   const DecodeGeom g = make_geom(c, B, K, T);
   // the sampling seed lives in device memory so that a captured graph can be replayed with a new seed
   c->launches += launch_set_u64((uint64_t*)c->d_seed.p, gp.seed, (uint64_t)gp.row_offset, s);
@@ -750,8 +773,80 @@ void do_generate(gstvd_ctx* c, int B, const gstvd_gen_params& gp, const int64_t*
     CUDA_CHECK(cudaGraphLaunch(it->second.exec, s));
     c->launches += it->second.kernels;
   }
-  if (gp.mode == GSTVD_SELECT_BEAM) c->launches += launch_beam_finalize(beam_buffers(c), B, K, T, 102, out_ids, out_scores, s);
-  else c->launches += launch_sample_finalize(B, T, 102, (const int32_t*)c->seq.p, out_ids, s);
+  generate_finalize(c, B, K, gp, out_ids, out_scores, s);
+}
+
+// One forward call of the decode branch of EncoderDecoderModel.forward (models/visual_dialog_model.py:24-120) - encoder, fusion,
+// cross-K/V prefill and every decode step - replayed from ONE CUDA graph per shape: the host enqueues a handful of device-to-device
+// copies of the inputs into context-owned buffers and one graph launch instead of ~350 kernels per round.  Same kernels, same
+// order, same results as gstvd_encode + gstvd_prefill_cross + gstvd_generate (asserted by the tests); eager when graphs are
+// disabled or while the GEMM profiler is on (events cannot be recorded inside a graph).
+void do_round(gstvd_ctx* c, int B, int Lt, int Lv, const int64_t* ids, const int64_t* seg, const float* att, const float* feat,
+              const float* loc, const float* imask, const gstvd_gen_params& gp, int64_t* out_ids, float* out_scores, cudaStream_t s) {
+  const int K = check_generate(c, gp, ids, seg ? seg : ids, Lt, out_ids);
+  if (B < 1 || B > c->B_max || Lt < 1 || Lt > c->Lt_max || Lv < 1 || Lv > c->Lv_max) throw InvalidArg("round: shape exceeds capacity");
+  if (!ids || !feat || !loc) throw InvalidArg("round: input_ids / image_feat / image_loc must not be NULL");
+  if (gp.ngram_blocking_size > 0 && !seg) throw InvalidArg("round: n-gram blocking needs token_type_ids");
+  const int T = gp.max_new_tokens, F = c->cfg.v_feature_size;
+  auto d2d = [&](void* dst, const void* src, size_t bytes) { if (src) CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s)); };
+  d2d(c->r_ids.p, ids, (size_t)B * Lt * 8); d2d(c->r_seg.p, seg, (size_t)B * Lt * 8); d2d(c->r_att.p, att, (size_t)B * Lt * 4);
+  d2d(c->r_feat.p, feat, (size_t)B * Lv * F * 4); d2d(c->r_loc.p, loc, (size_t)B * Lv * 5 * 4); d2d(c->r_imask.p, imask, (size_t)B * Lv * 4);
+  c->launches += launch_set_u64((uint64_t*)c->d_seed.p, gp.seed, (uint64_t)gp.row_offset, s);
+  const int64_t* g_ids = (const int64_t*)c->r_ids.p;
+  const int64_t* g_seg = seg ? (const int64_t*)c->r_seg.p : nullptr;
+  auto body = [&] {
+    do_encode(c, B, Lt, Lv, g_ids, g_seg, att ? (const float*)c->r_att.p : nullptr, (const float*)c->r_feat.p, (const float*)c->r_loc.p,
+              imask ? (const float*)c->r_imask.p : nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, s);
+    do_prefill(c, B, Lv + Lt, nullptr, nullptr, s);
+    const DecodeGeom g = make_geom(c, B, K, T);
+    if (gp.mode == GSTVD_SELECT_BEAM) c->launches += launch_beam_init(beam_buffers(c), B, K, T, 101, s);
+    else c->launches += launch_sample_init(B, T, 101, (int32_t*)c->seq.p, (int32_t*)c->cur_tokens.p, (int32_t*)c->prefix.p, T + 1, (int*)c->d_step.p, s);
+    for (int t = 0; t < T; ++t) decode_step(c, g, gp, g_ids, g_seg, Lt, s, t);
+    generate_finalize(c, B, K, gp, (int64_t*)c->r_out_ids.p, out_scores ? (float*)c->r_out_scores.p : nullptr, s);
+  };
+  const bool use_graph = !(c->cfg.flags & GSTVD_FLAG_NO_CUDA_GRAPH) && !c->profiling;
+  if (!use_graph) {
+    body();
+  } else {
+    gstvd_ctx::RoundKey key;
+    std::memset(&key, 0, sizeof key);
+    key.B = B; key.Lt = Lt; key.Lv = Lv; key.K = K; key.mode = gp.mode; key.T = T; key.top_k = gp.top_k; key.ngram = gp.ngram_blocking_size;
+    key.has_seg = seg != nullptr; key.has_att = att != nullptr; key.has_imask = imask != nullptr;
+    key.temperature = gp.temperature; key.top_p = gp.top_p;
+    if (out_scores) key.has_imask |= 2;
+    auto it = c->round_graphs.find(key);
+    if (it == c->round_graphs.end()) {
+      if (c->round_graphs.size() >= kMaxGraphs) {
+        auto victim = c->round_graphs.begin();
+        for (auto j = c->round_graphs.begin(); j != c->round_graphs.end(); ++j) if (j->second.last_use < victim->second.last_use) victim = j;
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        cudaGraphExecDestroy(victim->second.exec);
+        c->round_graphs.erase(victim);
+      }
+      const int64_t before = c->launches;
+      cudaGraph_t graph;
+      CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      try {
+        body();
+      } catch (...) {
+        cudaGraph_t dead; cudaStreamEndCapture(s, &dead);
+        throw;
+      }
+      CUDA_CHECK(cudaStreamEndCapture(s, &graph));
+      cudaGraphExec_t exec;
+      CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+      CUDA_CHECK(cudaGraphDestroy(graph));
+      it = c->round_graphs.emplace(key, gstvd_ctx::GraphEntry{exec, c->launches - before, 0}).first;
+      c->launches = before;
+    }
+    it->second.last_use = ++c->graph_clock;
+    CUDA_CHECK(cudaGraphLaunch(it->second.exec, s));
+    c->launches += it->second.kernels;
+    // host-side state the captured calls set (a replay does not run them again)
+    c->enc_B = B; c->enc_Le = Lv + Lt; c->cross_B = B; c->cross_Le = Lv + Lt;
+  }
+  CUDA_CHECK(cudaMemcpyAsync(out_ids, c->r_out_ids.p, (size_t)B * T * 8, cudaMemcpyDeviceToDevice, s));
+  if (out_scores) CUDA_CHECK(cudaMemcpyAsync(out_scores, c->r_out_scores.p, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
 }
 
 // `options` decoder sequences per image share that image's cross-attention K/V (evaluate_gen.py:62-107 re-encodes the same
@@ -908,12 +1003,14 @@ void gstvd_destroy(gstvd_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second.exec);
+  for (auto& kv : c->round_graphs) cudaGraphExecDestroy(kv.second.exec);
   DevBuf* bufs[] = {&c->mat32, &c->mat16, &c->vec32, &c->xt, &c->yt, &c->xv, &c->yv, &c->qkv_t, &c->qkv_v, &c->ctx_t, &c->ctx_v, &c->tmp_t,
                     &c->tmp_v, &c->ffn_t, &c->ffn_v, &c->feat_cast, &c->fused, &c->pool, &c->fused_mask, &c->dh, &c->da, &c->db, &c->dqkv,
                     &c->dctx, &c->dtmp, &c->dffn, &c->dqc, &c->logits, &c->cross_cache, &c->self_cache, &c->cross_len, &c->labels, &c->sel_val, &c->sel_idx,
                     &c->logz, &c->ban_tokens, &c->ban_count, &c->prefix, &c->seq, &c->beam_scores, &c->beam_tokens, &c->cur_tokens,
                     &c->beam_idx, &c->beam_done, &c->hyp_score, &c->hyp_len, &c->hyp_tokens, &c->hyp_count, &c->hyp_worst, &c->d_step, &c->d_seed, &c->anc, &c->fold16, &c->foldvec,
-                    &c->st1, &c->st2, &c->st3, &c->hist_ids_own, &c->hist_seg_own};
+                    &c->st1, &c->st2, &c->st3, &c->hist_ids_own, &c->hist_seg_own, &c->r_ids, &c->r_seg, &c->r_att,
+                    &c->r_feat, &c->r_loc, &c->r_imask, &c->r_out_ids, &c->r_out_scores};
   for (DevBuf* b : bufs) b->release();
   for (auto& r : c->prof_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (c->ev_in) cudaEventDestroy(c->ev_in);
@@ -959,6 +1056,8 @@ int gstvd_finalize_weights(gstvd_ctx* c, void* stream) {
     }
     for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second.exec);
     c->graphs.clear();
+    for (auto& kv : c->round_graphs) cudaGraphExecDestroy(kv.second.exec);
+    c->round_graphs.clear();
     c->finalized = true;
   });
 }
@@ -984,6 +1083,20 @@ int gstvd_generate(gstvd_ctx* c, int B, const gstvd_gen_params* params, const in
     CUDA_CHECK(cudaEventRecord(c->ev_in, user));
     CUDA_CHECK(cudaStreamWaitEvent(c->own_stream, c->ev_in, 0));
     do_generate(c, B, *params, hist_ids, hist_segments, Lh, out_ids, out_scores, c->own_stream);
+    CUDA_CHECK(cudaEventRecord(c->ev_out, c->own_stream));
+    CUDA_CHECK(cudaStreamWaitEvent(user, c->ev_out, 0));
+  });
+}
+
+int gstvd_round(gstvd_ctx* c, int B, int Lt, int Lv, const int64_t* input_ids, const int64_t* token_type_ids, const float* attention_mask,
+                const float* image_feat, const float* image_loc, const float* image_mask, const gstvd_gen_params* params, int64_t* out_ids,
+                float* out_scores, void* stream) {
+  if (!c || !params) { g_last_error = "gstvd_round: NULL argument"; return GSTVD_ERR_INVALID; }
+  return guarded(c, [&] {
+    cudaStream_t user = (cudaStream_t)stream;
+    CUDA_CHECK(cudaEventRecord(c->ev_in, user));
+    CUDA_CHECK(cudaStreamWaitEvent(c->own_stream, c->ev_in, 0));
+    do_round(c, B, Lt, Lv, input_ids, token_type_ids, attention_mask, image_feat, image_loc, image_mask, *params, out_ids, out_scores, c->own_stream);
     CUDA_CHECK(cudaEventRecord(c->ev_out, c->own_stream));
     CUDA_CHECK(cudaStreamWaitEvent(user, c->ev_out, 0));
   });

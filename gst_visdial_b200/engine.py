@@ -183,6 +183,31 @@ class Engine:
                                                 self._stream()))
         return (out, scores) if want_scores else out
 
+    def round(self, input_ids, image_feat, image_loc, token_type_ids=None, attention_mask=None, image_mask=None, num_beams=1,
+              temperature=1.0, top_k=1, top_p=0.0, ngram_blocking_size=0, seed=0, max_new_tokens=None, want_scores=False, row_offset=0):
+        """encode + prefill_cross + generate of one forward call as ONE graph replay (gstvd_round); the n-gram blocking history is
+        ``input_ids`` / ``token_type_ids``.  Leaves the encoder / cross-K/V state resident like the three separate calls."""
+        ids = self._dev(input_ids, torch.int64)
+        B, Lt = ids.shape
+        feat = self._dev(image_feat, torch.float32)
+        Lv = feat.shape[1]
+        loc = self._dev(image_loc, torch.float32)
+        seg = self._dev(token_type_ids, torch.int64)
+        att = self._dev(attention_mask, torch.float32)
+        imask = self._dev(image_mask, torch.float32)
+        gp = GstvdGenParams()
+        gp.mode = GSTVD_SELECT_BEAM if num_beams > 1 else GSTVD_SELECT_SAMPLE
+        gp.num_beams = int(num_beams)
+        gp.max_new_tokens = int(max_new_tokens or self.max_new_tokens)
+        gp.top_k, gp.temperature, gp.top_p = int(top_k), float(temperature), float(top_p)
+        gp.ngram_blocking_size, gp.seed = int(ngram_blocking_size), int(seed) & (2**64 - 1)
+        gp.row_offset = int(row_offset)
+        out = torch.empty(B, gp.max_new_tokens, device=self.device, dtype=torch.int64)
+        scores = torch.empty(B, device=self.device, dtype=torch.float32) if want_scores else None
+        check(self.ctx, self.lib.gstvd_round(self.ctx, B, Lt, Lv, _ptr(ids), _ptr(seg), _ptr(att), _ptr(feat), _ptr(loc), _ptr(imask),
+                                             ctypes.byref(gp), _ptr(out), _ptr(scores), self._stream()))
+        return (out, scores) if want_scores else out
+
     def score(self, dec_ids, dec_mask=None, labels=None, want_logits=False, want_loss=True, options_per_image=1):
         """``dec_ids`` (int64, on the engine's device, contiguous) is mutated in place when ``labels`` is None.
         ``options_per_image`` > 1: rows are option-major per image and share the image's cross-attention K/V."""

@@ -111,18 +111,23 @@ class EncoderDecoderModel(_EngineOwner, nn.Module):
     ):
         eng = self._engine(enc_input_ids.device)
         B = enc_input_ids.shape[0]
-        if not decoding_kwargs.get("reuse_encoder", False):
+        reuse = decoding_kwargs.get("reuse_encoder", False)
+        decode = not ('train' in self.params['mode'] or 'eval' in self.params['mode'])
+        ids_e, seg_e, att_e = enc_input_ids, enc_segments, enc_attention_mask
+        if not reuse:
             hint = decoding_kwargs.get("enc_valid_len")
-            ids_e, seg_e, att_e = enc_input_ids, enc_segments, enc_attention_mask
             if hint is not None:
                 Lt = enc_input_ids.shape[1]
                 Lt_eff = min(Lt, max(32, (int(hint) + 31) // 32 * 32))
                 if Lt_eff < Lt:
                     ids_e, seg_e, att_e = ids_e[:, :Lt_eff], seg_e[:, :Lt_eff], (att_e[:, :Lt_eff] if att_e is not None else None)
+        # decode mode, fresh encoder inputs: the whole call (encoder, fusion, cross-K/V prefill, 18 decode steps) is ONE graph replay
+        whole_round = decode and not reuse and self.params.get("engine_round_graph", True) and enc_segments is not None
+        if not reuse and not whole_round:
             enc = eng.encode(ids_e, enc_image_features, enc_image_spatials, seg_e, att_e, enc_image_mask)
             eng.prefill_cross(B, enc["Le"])
 
-        if 'train' in self.params['mode'] or 'eval' in self.params['mode']:
+        if not decode:
             out = self._score(eng, dec_input_ids, dec_attention_mask, dec_labels, loss_reduction,
                               want_logits=decoding_kwargs.get("want_logits", True))
             return out.loss, out.logits
@@ -137,8 +142,7 @@ class EncoderDecoderModel(_EngineOwner, nn.Module):
             # teacher must not replay the same uniforms) and this model's call counter.  Callers that want draws that do not
             # depend on the batch / rank split pass seed= and row_offset= themselves (gst_visdial_b200/dialog.py does).
             seed = derive_seed(self.params.get("seed", 0), self.params.get("model", ""), self._calls)
-        return eng.generate(
-            B,
+        gen_kw = dict(
             num_beams=int(decoding_kwargs.get("num_beams", 1)),
             temperature=decoding_kwargs['temperature'],
             top_k=decoding_kwargs['top_k'],
@@ -146,9 +150,11 @@ class EncoderDecoderModel(_EngineOwner, nn.Module):
             ngram_blocking_size=decoding_kwargs['ngram_blocking_size'],
             seed=seed,
             row_offset=int(decoding_kwargs.get("row_offset", 0)),
-            hist_ids=enc_input_ids,
-            hist_segments=enc_segments,
         )
+        if whole_round:
+            # the n-gram blocking history is the (trimmed) encoder input itself: positions past the bound hold no token
+            return eng.round(ids_e, enc_image_features, enc_image_spatials, seg_e, att_e, enc_image_mask, **gen_kw)
+        return eng.generate(B, hist_ids=enc_input_ids, hist_segments=enc_segments, **gen_kw)
 
     def _check_decoder_start(self, dec_input_ids):
         """The reference continues from whatever prefix the caller passes (models/visual_dialog_model.py:86-110); every caller on

@@ -147,6 +147,16 @@ int gstvd_generate(gstvd_ctx* ctx, int B, const gstvd_gen_params* params,
                    const int64_t* hist_ids, const int64_t* hist_segments, int Lh,
                    int64_t* out_ids, float* out_scores, void* stream);
 
+/* One whole forward call of the decode branch of EncoderDecoderModel.forward (models/visual_dialog_model.py:24-120): the same work and
+ * results as gstvd_encode (no exported outputs) + gstvd_prefill_cross(resident states) + gstvd_generate, replayed from ONE CUDA graph
+ * per shape - the host enqueues a few device-to-device copies of the inputs and one graph launch.  The n-gram blocking history is the
+ * call's own input_ids / token_type_ids.  Afterwards the encoder / cross-K/V state is resident exactly as after the three calls (e.g.
+ * for the perplexity pass, gstvd_score). */
+int gstvd_round(gstvd_ctx* ctx, int B, int Lt, int Lv,
+                const int64_t* input_ids, const int64_t* token_type_ids, const float* attention_mask,
+                const float* image_feat, const float* image_loc, const float* image_mask,
+                const gstvd_gen_params* params, int64_t* out_ids, float* out_scores, void* stream);
+
 /* Replaces VisualDialogDecoder.forward in loss mode (models/visual_dialog_decoder.py:33-86) as driven by
  * generate.py:183-209 and evaluate_gen.py:94-106: teacher-forced pass over dec_ids [B, L].
  *   dec_ids  : int64 [B, L]; when labels == NULL it is MUTATED IN PLACE ([SEP] -> PAD) exactly like :57 and the

@@ -277,3 +277,35 @@ def test_config4_config5_helpers_are_exact_under_trimming_and_chunking(tiny_cfgs
     want = RK.nsp_rank(enc, flat, device="cuda:0").reshape(3, 5)
     assert got.shape == (3, 5) and torch.equal(got, want)
     assert ((got > 0) & (got < 1)).all()
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_whole_round_graph_equals_separate_calls(tiny_cfgs, tiny_sd, dtype):
+    """gstvd_round (encoder + fusion + cross-K/V prefill + all decode steps as ONE graph replay) against gstvd_encode +
+    gstvd_prefill_cross + gstvd_generate: identical token ids in greedy, beam-5 and seeded sampling with 4-gram blocking, on trimmed
+    and full-length inputs, on the first call (capture) and on replays; the resident state serves a following perplexity pass."""
+    from gst_visdial_b200.engine import Engine
+    enc_cfg, dec_cfg = tiny_cfgs
+    B = 3
+    b = history_batch(enc_cfg, 0, B)
+    e = Engine(enc_cfg, dec_cfg, dtype=dtype, max_batch=4, max_beams=5)
+    e.load_state_dict(tiny_sd)
+    dev = {k: v.cuda() for k, v in b.items()}
+    for Lt in (256, 96):
+        ids, seg, att = dev["enc_input_ids"][:, :Lt].contiguous(), dev["enc_segments"][:, :Lt].contiguous(), dev["enc_att_mask"][:, :Lt].contiguous()
+        assert int((dev["enc_input_ids"][:, Lt:] != 0).sum()) == 0
+        for kw in (dict(num_beams=1, top_k=1), dict(num_beams=5), dict(num_beams=1, top_k=7, temperature=0.7, ngram_blocking_size=4, seed=5, row_offset=11)):
+            o = e.encode(ids, dev["enc_image_feat"], dev["enc_image_loc"], seg, att, dev["enc_image_mask"])
+            e.prefill_cross(B, o["Le"])
+            want = e.generate(B, hist_ids=ids, hist_segments=seg, **kw).cpu()
+            for rep in range(2):                                      # capture, then replay
+                got = e.round(ids, dev["enc_image_feat"], dev["enc_image_loc"], seg, att, dev["enc_image_mask"], **kw).cpu()
+                assert torch.equal(got, want), (dtype, Lt, kw, rep)
+        # the round leaves encoder / cross-K/V state resident: a teacher-forced pass right after it equals one after encode + prefill
+        ans = want.cuda().clone()
+        l_round, _ = e.score(ans.clone(), (ans != 0).float())
+        o = e.encode(ids, dev["enc_image_feat"], dev["enc_image_loc"], seg, att, dev["enc_image_mask"])
+        e.prefill_cross(B, o["Le"])
+        l_sep, _ = e.score(ans.clone(), (ans != 0).float())
+        assert torch.equal(l_round, l_sep)
+    e.close()
