@@ -273,8 +273,24 @@ int launch_attention_mma(const AttnArgs& a, cudaStream_t stream) {
   if (a.B <= 0 || a.Lq <= 0) return 0;
   if (!attention_mma_supported(a)) throw std::runtime_error("attention_mma: unsupported shape / alignment");
   if (a.D == 64) {
-    if (a.Lq > 64) launch_d<64, 8>(a, stream);                    // 128-query tiles: K / V stream through shared memory half as often
-    else launch_d<64, 4>(a, stream);
+    // Query tile = 16 * QW rows.  Big tiles stream K / V through shared memory less often, but a tile that sticks out past Lq is
+    // wasted math: the dialog loop trims the text to multiples of 32 tokens, so e.g. Lq = 160 is two exact 80-row tiles (QW = 5)
+    // instead of 128 + 32 of 128.  Pick the QW in 4..8 with the fewest padded rows, the larger one on ties.
+    int best = 4;
+    if (a.Lq > 64) {
+      int best_pad = 1 << 30;
+      for (int qw = 8; qw >= 4; --qw) {
+        const int t = qw * 16, pad = (a.Lq + t - 1) / t * t - a.Lq;
+        if (pad < best_pad) { best_pad = pad; best = qw; }
+      }
+    }
+    switch (best) {
+      case 8: launch_d<64, 8>(a, stream); break;
+      case 7: launch_d<64, 7>(a, stream); break;
+      case 6: launch_d<64, 6>(a, stream); break;
+      case 5: launch_d<64, 5>(a, stream); break;
+      default: launch_d<64, 4>(a, stream); break;
+    }
   } else {
     launch_d<128, 4>(a, stream);
   }

@@ -157,7 +157,10 @@ def test_attention(eng, dtype, tol, B, heads, Lq, Lk, D, causal, neg):
 
 
 @pytest.mark.parametrize("heads,Lq,Lk,D,causal", [(12, 256, 256, 64, False), (8, 37, 256, 128, False), (8, 256, 37, 128, False), (12, 25, 293, 64, False),
-                                                  (12, 130, 130, 64, True)])
+                                                  (12, 130, 130, 64, True),
+                                                  # trimmed history lengths: query tiles of 80 / 96 / 112 rows (QW = 5, 6, 7)
+                                                  (12, 160, 160, 64, False), (12, 192, 192, 64, False), (12, 224, 224, 64, False),
+                                                  (12, 96, 96, 64, False), (12, 100, 100, 64, True)])
 def test_attention_trailing_padding_bf16(eng, heads, Lq, Lk, D, causal):
     """History-shaped masks (valid prefix, padded tail): the tensor-core kernel skips key tiles past the last valid key."""
     g = torch.Generator().manual_seed(Lq + 7 * Lk)
