@@ -681,10 +681,17 @@ void decode_step(gstvd_ctx* c, const DecodeGeom& g, const gstvd_gen_params& gp, 
                                       (int32_t*)c->ban_tokens.p, (int32_t*)c->ban_count.p, Lh, s);
       bt = (const int32_t*)c->ban_tokens.p; bc = (const int32_t*)c->ban_count.p;
     }
-    c->launches += launch_row_select(M, c->V, (const float*)c->logits.p, c->Vpad, 1, nullptr, gp.temperature, bt, bc, Lh, nsel, sv, si,
-                                     nullptr, s);
-    c->launches += launch_sample_step(M, g.T, nsel, sv, si, gp.top_k, gp.top_p, 0, 0, (const uint64_t*)c->d_seed.p, d_step, 102, (int32_t*)c->seq.p,
-                                      (int32_t*)c->cur_tokens.p, (int32_t*)c->prefix.p, g.T + 1, nullptr, s);
+    if (gp.top_k == 0) {
+      // no top-k cut (utils/decoding_utils.py:17 skips it): multinomial over the whole, optionally nucleus-filtered, vocabulary
+      c->launches += launch_full_vocab_sample(M, c->V, (const float*)c->logits.p, c->Vpad, gp.temperature, gp.top_p, bt, bc, Lh, g.T, 0, 0,
+                                              (const uint64_t*)c->d_seed.p, d_step, 102, (int32_t*)c->seq.p, (int32_t*)c->cur_tokens.p,
+                                              (int32_t*)c->prefix.p, g.T + 1, nullptr, s);
+    } else {
+      c->launches += launch_row_select(M, c->V, (const float*)c->logits.p, c->Vpad, 1, nullptr, gp.temperature, bt, bc, Lh, nsel, sv, si,
+                                       nullptr, s);
+      c->launches += launch_sample_step(M, g.T, nsel, sv, si, gp.top_k, gp.top_p, 0, 0, (const uint64_t*)c->d_seed.p, d_step, 102, (int32_t*)c->seq.p,
+                                        (int32_t*)c->cur_tokens.p, (int32_t*)c->prefix.p, g.T + 1, nullptr, s);
+    }
   }
   c->launches += launch_step_advance((int*)c->d_step.p, s);
 }
@@ -702,7 +709,8 @@ int check_generate(gstvd_ctx* c, const gstvd_gen_params& gp, const int64_t* hist
     if (K < 1 || K > c->K_max || 2 * K > kSelMax) throw InvalidArg("generate: num_beams out of range");
     if (gp.ngram_blocking_size > 0) throw Unsupported("generate: n-gram blocking is only implemented for GSTVD_SELECT_SAMPLE");
   } else if (gp.mode == GSTVD_SELECT_SAMPLE) {
-    if (gp.top_k < 1 || gp.top_k > GSTVD_MAX_TOP_K) throw Unsupported("generate: top_k must be in 1..16 (top_k = 0 / pure nucleus is not implemented)");
+    if (gp.top_k < 0 || gp.top_k > GSTVD_MAX_TOP_K) throw Unsupported("generate: top_k must be 0 (no top-k cut) or in 1..16");
+    if (gp.top_k == 0 && c->V > 32768) throw Unsupported("generate: top_k = 0 needs a vocabulary of at most 32768 entries");
     if (!(gp.temperature > 0.f)) throw InvalidArg("generate: temperature must be > 0");
     if (gp.ngram_blocking_size > 0 && (!hist_ids || !hist_seg || Lh < 1 || Lh > c->Lt_max)) throw InvalidArg("generate: n-gram blocking needs hist_ids / hist_segments");
   } else {
@@ -1381,7 +1389,8 @@ int gstvd_op_sample(gstvd_ctx* c, int rows, const float* logits, int64_t ldl, co
   return guarded(c, [&] {
     if (c->dec_layers == 0) throw StateError("sample op needs a decoder context");
     if (rows < 1 || rows > c->B_max) throw InvalidArg("op_sample: rows out of range");
-    if (gp->top_k < 1 || gp->top_k > GSTVD_MAX_TOP_K) throw Unsupported("op_sample: top_k must be in 1..16");
+    if (gp->top_k < 0 || gp->top_k > GSTVD_MAX_TOP_K) throw Unsupported("op_sample: top_k must be 0 (no top-k cut) or in 1..16");
+    if (gp->top_k == 0 && c->V > 32768) throw Unsupported("op_sample: top_k = 0 needs a vocabulary of at most 32768 entries");
     cudaStream_t s = (cudaStream_t)stream;
     const int T = c->T_max;
     CUDA_CHECK(cudaMemcpyAsync(c->d_step.p, &step, 4, cudaMemcpyHostToDevice, s));
@@ -1395,6 +1404,12 @@ int gstvd_op_sample(gstvd_ctx* c, int rows, const float* logits, int64_t ldl, co
       c->launches += launch_ngram_ban(rows, Lh, hist_ids, hist_segments, (const int32_t*)c->prefix.p, T + 1, (const int*)c->d_step.p,
                                       gp->ngram_blocking_size, (int32_t*)c->ban_tokens.p, (int32_t*)c->ban_count.p, Lh, s);
       bt = (const int32_t*)c->ban_tokens.p; bc = (const int32_t*)c->ban_count.p;
+    }
+    if (gp->top_k == 0) {
+      c->launches += launch_full_vocab_sample(rows, c->V, logits, ldl, gp->temperature, gp->top_p, bt, bc, Lh, T, gp->seed, (uint64_t)gp->row_offset, nullptr,
+                                              (const int*)c->d_step.p, 102, (int32_t*)c->seq.p, (int32_t*)c->cur_tokens.p, (int32_t*)c->prefix.p, T + 1,
+                                              out_tokens, s);
+      return;
     }
     c->launches += launch_row_select(rows, c->V, logits, ldl, 1, nullptr, gp->temperature, bt, bc, Lh, kSelMax, (float*)c->sel_val.p,
                                      (int32_t*)c->sel_idx.p, nullptr, s);

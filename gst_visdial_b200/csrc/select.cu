@@ -655,6 +655,142 @@ __global__ void sample_step_kernel(int rows, int T, int nsel, const float* __res
   if (out_tokens) out_tokens[row] = tok;
 }
 
+// ---- top_k = 0: unrestricted / pure-nucleus multinomial over the whole vocabulary (utils/decoding_utils.py:17-35 with top_k == 0,
+// then softmax + torch.multinomial, models/visual_dialog_model.py:100-105) ---------------------------------------------------------
+// One CTA per row; thread t owns the 32 consecutive tokens [32 t, 32 t + 32) in registers (V <= 32768).
+//   x = logit / temperature, banned tokens -> -inf;  p = exp(x - max);  Z = sum p
+//   nucleus (top_p > 0): the reference sorts descending and removes position r when the cumulative probability of positions 0..r-1
+//     exceeds top_p, i.e. a token survives iff  S(x) = sum of p over tokens with a strictly larger logit  <=  top_p Z.  S is monotone
+//     in x, so the survivors are {x >= x*}; x* is found by a 32-step bit-wise search over the order-preserving integer image of the
+//     float (no sort).  Tokens with bit-identical logits survive or fall together (torch.sort leaves their order undefined).
+//   draw: u Z_kept located by a block-wide exclusive scan of the per-thread sums in token order (the distribution does not depend on
+//     the order in which the survivors are laid out).  All reductions run in a fixed order: deterministic for a given seed.
+constexpr int kFvThreads = 1024, kFvPer = 32;
+__device__ __forceinline__ uint32_t float_order_key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float fv_block_sum(float v, float* s_red) {      // every thread gets the total; fixed order
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  float t = s_red[lane];
+  t = warp_sum(t);
+  return t;
+}
+__global__ void __launch_bounds__(kFvThreads)
+full_vocab_sample_kernel(int V, const float* __restrict__ logits, int64_t ldl, float temperature, float top_p,
+                         const int32_t* __restrict__ ban_tokens, const int32_t* __restrict__ ban_count, int ban_stride,
+                         int T, uint64_t seed, uint64_t row_offset, const uint64_t* __restrict__ d_seed, const int* __restrict__ d_step, int eos,
+                         int32_t* seq, int32_t* cur_tokens, int32_t* prefix, int prefix_stride, int32_t* out_tokens) {
+  extern __shared__ float s_p[];                   // [kFvPer][kFvThreads]: p of token 32 t + j at s_p[j * 1024 + t] (conflict free)
+  __shared__ float s_red[32];
+  __shared__ float s_scan[32];
+  __shared__ int s_choice;
+  pdl_wait();
+  pdl_launch_dependents();
+  const int row = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int step = *d_step;
+  const float* x = logits + (int64_t)row * ldl;
+  const int base = tid * kFvPer;
+  float v[kFvPer];
+#pragma unroll
+  for (int j = 0; j < kFvPer; ++j) v[j] = (base + j < V) ? __fdiv_rn(x[base + j], temperature) : -INFINITY;
+  if (ban_tokens != nullptr) {
+    const int nb = ban_count[row];
+    for (int i = 0; i < nb; ++i) {
+      const int tk = ban_tokens[(int64_t)row * ban_stride + i];
+      if (tk >= base && tk < base + kFvPer) {
+#pragma unroll
+        for (int j = 0; j < kFvPer; ++j) if (base + j == tk) v[j] = -INFINITY;
+      }
+    }
+  }
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kFvPer; ++j) m = fmaxf(m, v[j]);
+  m = warp_max(m);
+  if (lane == 0) s_red[warp] = m;
+  __syncthreads();
+  m = warp_max(s_red[lane]);
+  float local = 0.f;
+#pragma unroll
+  for (int j = 0; j < kFvPer; ++j) { const float pj = (v[j] > -INFINITY) ? expf(v[j] - m) : 0.f; s_p[j * kFvThreads + tid] = pj; local += pj; }
+  float total = fv_block_sum(local, s_red);
+  if (top_p > 0.f) {
+    const float budget = top_p * total;
+    // largest r with S(r) > budget (S(0) > budget unless the whole mass sits on the smallest key); survivors: key >= r + 1
+    uint32_t r = 0;
+    bool any_false;
+    {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < kFvPer; ++j) s += float_order_key(v[j]) > 0u ? s_p[j * kFvThreads + tid] : 0.f;
+      any_false = fv_block_sum(s, s_red) > budget;
+    }
+    if (any_false) {                               // block-uniform: every thread holds the same total
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t c = r | (1u << bit);
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < kFvPer; ++j) s += float_order_key(v[j]) > c ? s_p[j * kFvThreads + tid] : 0.f;
+        if (fv_block_sum(s, s_red) > budget) r = c;
+      }
+      const uint32_t kmin = r + 1u;
+      local = 0.f;
+#pragma unroll
+      for (int j = 0; j < kFvPer; ++j) {
+        if (float_order_key(v[j]) < kmin) s_p[j * kFvThreads + tid] = 0.f;
+        local += s_p[j * kFvThreads + tid];
+      }
+      total = fv_block_sum(local, s_red);
+    }
+  }
+  // draw: first token (in index order) whose inclusive prefix sum exceeds u * total
+  const uint64_t sd = d_seed ? d_seed[0] : seed;
+  const uint64_t grow = (uint64_t)row + (d_seed ? d_seed[1] : row_offset);
+  const uint64_t h = splitmix64(sd ^ splitmix64((grow << 20) ^ (uint64_t)step));
+  const float target = (float)(h >> 40) * (1.0f / 16777216.0f) * total;
+  float incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+  __syncthreads();
+  if (lane == 31) s_scan[warp] = incl;
+  if (tid == 0) s_choice = -1;
+  __syncthreads();
+  float woff = 0.f;
+  for (int w = 0; w < warp; ++w) woff += s_scan[w];                 // fixed order
+  const float excl = woff + incl - local;
+  if (local > 0.f && target >= excl && target < excl + local) {
+    float c = excl; int pick = -1, last = -1;
+#pragma unroll
+    for (int j = 0; j < kFvPer; ++j) {
+      const float pj = s_p[j * kFvThreads + tid];
+      if (pj > 0.f) { c += pj; last = base + j; if (pick < 0 && target < c) pick = base + j; }
+    }
+    atomicMax(&s_choice, pick < 0 ? last : pick);                    // rounding at the end of the range: last survivor of this thread
+  }
+  __syncthreads();
+  const int found = s_choice;
+  __syncthreads();
+  if (found < 0) {                                                   // rounding pushed the target past every range: last survivor overall
+    int last = -1;
+#pragma unroll
+    for (int j = 0; j < kFvPer; ++j) if (s_p[j * kFvThreads + tid] > 0.f) last = base + j;
+    if (last >= 0) atomicMax(&s_choice, last);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const int tok = s_choice < 0 ? 0 : s_choice;
+    if (step < T) seq[(int64_t)row * T + step] = tok;
+    cur_tokens[row] = tok;
+    if (step + 1 < prefix_stride) prefix[(int64_t)row * prefix_stride + step + 1] = (tok == eos) ? 0 : tok;
+    if (out_tokens) out_tokens[row] = tok;
+  }
+}
+
 __global__ void sample_finalize_kernel(int rows, int T, int eos, const int32_t* __restrict__ seq, int64_t* __restrict__ out_ids) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
@@ -791,6 +927,23 @@ int launch_sample_step(int rows, int T, int nsel, const float* sel_val, const in
   if (top_k < 1 || top_k > nsel) throw std::runtime_error("sample_step: top_k out of range");
   launch_k(sample_step_kernel, dim3((rows + 63) / 64), dim3(64), 0, stream, rows, T, nsel, sel_val, sel_idx, top_k, top_p, seed, row_offset, d_seed, d_step, eos, seq,
                                                           cur_tokens, prefix, prefix_stride, out_tokens);
+  return 1;
+}
+int launch_full_vocab_sample(int rows, int V, const float* logits, int64_t ldl, float temperature, float top_p, const int32_t* ban_tokens,
+                             const int32_t* ban_count, int ban_stride, int T, uint64_t seed, uint64_t row_offset, const uint64_t* d_seed,
+                             const int* d_step, int eos, int32_t* seq, int32_t* cur_tokens, int32_t* prefix, int prefix_stride, int32_t* out_tokens,
+                             cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (V > kFvThreads * kFvPer) throw std::runtime_error("full_vocab_sample: vocab > 32768");
+  constexpr size_t smem = (size_t)kFvThreads * kFvPer * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(full_vocab_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("full_vocab_sample: cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    attr_set = true;
+  }
+  launch_k(full_vocab_sample_kernel, dim3(rows), dim3(kFvThreads), smem, stream, V, logits, ldl, temperature, top_p, ban_tokens, ban_count, ban_stride,
+           T, seed, row_offset, d_seed, d_step, eos, seq, cur_tokens, prefix, prefix_stride, out_tokens);
   return 1;
 }
 int launch_sample_init(int rows, int T, int start_token, int32_t* seq, int32_t* cur_tokens, int32_t* prefix,

@@ -83,7 +83,8 @@ typedef struct {
   int32_t mode;               /* gstvd_select_mode */
   int32_t num_beams;          /* beam mode: K (<= max_beams); sample mode: ignored (1 row per image) */
   int32_t max_new_tokens;     /* <= config.max_new_tokens */
-  int32_t top_k;              /* sample mode; 1 = greedy; must be 1..GSTVD_MAX_TOP_K */
+  int32_t top_k;              /* sample mode; 1 = greedy; 2..GSTVD_MAX_TOP_K = top-k set (ties kept); 0 = no top-k cut: multinomial over the
+                                 whole - optionally nucleus-filtered - vocabulary (utils/decoding_utils.py:17 skips the cut) */
   float temperature;          /* sample mode: logits / temperature */
   float top_p;                /* sample mode: nucleus threshold applied inside the top-k set; 0 = off */
   int32_t ngram_blocking_size;/* 0 = off; n: ban tokens completing an n-gram of the question history */

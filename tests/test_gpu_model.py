@@ -592,8 +592,11 @@ def test_capacity_and_state_errors_are_reported(tiny_cfgs, tiny_sd):
         e.generate(2, num_beams=5)
     with pytest.raises(GstvdError):                       # prefilled for 2 images, asked for 1
         e.generate(1, num_beams=2)
-    with pytest.raises(GstvdError):                       # top_k = 0 (pure nucleus) is documented as unsupported
-        e.generate(2, num_beams=1, top_k=0, top_p=0.9, temperature=1.0)
+    with pytest.raises(GstvdError):                       # top_k outside 0..16
+        e.generate(2, num_beams=1, top_k=17, top_p=0.9, temperature=1.0)
+    ids0 = e.generate(2, num_beams=1, top_k=0, top_p=0.9, temperature=1.0, seed=3)   # top_k = 0: pure nucleus over the vocabulary
+    assert ids0.shape == (2, 18) and int(ids0.min()) >= 0 and int(ids0.max()) < enc_cfg.vocab_size
+    assert torch.equal(ids0, e.generate(2, num_beams=1, top_k=0, top_p=0.9, temperature=1.0, seed=3))
     ids = e.generate(2, num_beams=2)                      # and the context still works afterwards
     assert ids.shape == (2, 18)
     e.close()

@@ -153,6 +153,65 @@ def test_nucleus_filter_matches_reference(tiny_cfgs, tiny_sd, top_k, top_p, temp
     e.close()
 
 
+@pytest.mark.parametrize("cfg", ["tiny", "full"])
+def test_full_vocabulary_sampling_matches_reference(tiny_cfgs, tiny_sd, full_cfgs, full_sd, cfg):
+    """top_k = 0 (utils/decoding_utils.py:17 skips the top-k cut): pure nucleus (top_p > 0) or unrestricted multinomial (top_p = 0)
+    over the whole vocabulary - the branch the reference supports but its callers never take.  The support of the device sampler
+    must equal the set the reference's filter keeps (sort + cumsum, :23-35) and the empirical distribution must match softmax of
+    the survivors (models/visual_dialog_model.py:104-105).  Vocabulary 1000 (tiny) and 30 522 (full; one thread owns 32 tokens)."""
+    from gst_visdial_b200.engine import Engine
+    enc_cfg, dec_cfg = tiny_cfgs if cfg == "tiny" else full_cfgs
+    e = Engine(enc_cfg, dec_cfg, dtype="bf16" if cfg == "full" else "fp32", max_batch=8)
+    e.load_state_dict(tiny_sd if cfg == "tiny" else full_sd)
+    V = enc_cfg.vocab_size
+    for top_p, temperature in [(0.9, 1.0), (0.5, 0.7), (0.05, 1.0), (0.0, 1.0), (0.0, 0.6)]:
+        g = torch.Generator().manual_seed(int(top_p * 100) + int(temperature * 10) + V)
+        rows = 4
+        logits = torch.randn(rows, V, generator=g) * 3.0
+        logits[1, 5] = logits[1].max() + 14.0            # a peaked row: the nucleus is a single token
+        logits[2] = torch.randn(V, generator=g) * 8.0     # a row with a small nucleus
+        dev_logits = logits.cuda()
+        ref = R.top_k_top_p_filter(logits.clone() / temperature, top_k=0, top_p=top_p)
+        keep = [set(torch.nonzero(torch.isfinite(ref[r])).flatten().tolist()) for r in range(rows)]
+        probs = torch.softmax(ref, -1)
+        n_draws = 2000
+        counts = torch.zeros(rows, V)
+        for seed in range(n_draws):
+            tok = e.op_sample(dev_logits, step=0, temperature=temperature, top_k=0, top_p=top_p, seed=seed).cpu().long()
+            counts[torch.arange(rows), tok] += 1
+        for r in range(rows):
+            drawn = set(torch.nonzero(counts[r]).flatten().tolist())
+            assert drawn <= keep[r], f"row {r}: sampled tokens {sorted(drawn - keep[r])[:8]} outside the reference nucleus ({len(keep[r])} tokens)"
+            emp = counts[r] / n_draws
+            likely = {t for t in keep[r] if probs[r, t] > 1e-2}
+            assert likely <= drawn, f"row {r}: likely tokens never drawn: {sorted(likely - drawn)}"
+            assert float((emp - probs[r]).abs().max()) < 0.045, f"row {r}: empirical distribution off by {float((emp - probs[r]).abs().max()):.3f}"
+            # total-variation distance over the 64 likeliest tokens + the rest (a wrong scan order / offset shows up here)
+            top = torch.topk(probs[r], min(64, V)).indices
+            tv = 0.5 * ((emp[top] - probs[r, top]).abs().sum() + abs(float(emp.sum() - emp[top].sum()) - float(1.0 - probs[r, top].sum())))
+            assert float(tv) < 0.15, f"row {r}: total variation {float(tv):.3f}"
+        if top_p > 0:
+            assert len(keep[1]) == 1
+        # same seed -> same tokens
+        a = e.op_sample(dev_logits, step=0, temperature=temperature, top_k=0, top_p=top_p, seed=7).cpu()
+        assert torch.equal(a, e.op_sample(dev_logits, step=0, temperature=temperature, top_k=0, top_p=top_p, seed=7).cpu())
+    # the n-gram ban list (utils/decoding_utils.py:38-78) is honoured by this path as well: history "... 5 6 7 8 [SEP]", decoded prefix
+    # [CLS] 5 6 7 -> token 8 is banned although it carries almost all of the probability mass
+    Lh = 16
+    hist = torch.zeros(2, Lh, dtype=torch.int64)
+    hist[:, :7] = torch.tensor([101, 9, 5, 6, 7, 8, 102])
+    seg = torch.zeros(2, Lh, dtype=torch.int64)
+    prefix = torch.tensor([[101, 5, 6, 7], [101, 5, 6, 9]], dtype=torch.int64)
+    lg = torch.zeros(2, V)
+    lg[:, 8] = 30.0
+    lg[:, 11] = 28.0
+    toks = torch.stack([e.op_sample(lg.cuda(), step=3, temperature=1.0, top_k=0, top_p=tp, ngram_blocking_size=4, seed=sd, hist_ids=hist,
+                                    hist_segments=seg, prefix=prefix).cpu() for sd in range(50) for tp in (0.0, 0.9)])
+    assert (toks[:, 0] != 8).all() and (toks[:, 0] == 11).float().mean() > 0.9, toks[:, 0]     # banned in row 0 ...
+    assert (toks[:, 1] == 8).float().mean() > 0.7, toks[:, 1]                                   # ... not in row 1 (prefix ends 6 9)
+    e.close()
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_reorder_cache_matches_index_select(tiny_cfgs, tiny_sd, dtype):
     """gstvd_reorder_cache == past_state.index_select(0, beam_idx) for every tensor of every layer
