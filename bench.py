@@ -311,7 +311,7 @@ def make_slot(a, si, rank, world, dev, local, enc_cfg, dec_cfg, sds):
     S_ = a.streams
     start = (rank * S_ + si) * B                       # weak scaling: every rank / stream owns its own images
     base = {"model_enc_config": W.DEFAULT_ENC_CONFIG, "model_dec_config": W.DEFAULT_DEC_CONFIG, "gpu_ids": [local], "mode": "cc12m_gen",
-            "compute_dtype": a.dtype, "engine_max_batch": B, "engine_max_beams": max(a.beams, 1), "engine_flags": 0, "seed": 0}
+            "compute_dtype": a.dtype, "engine_max_batch": B, "engine_max_beams": max(a.beams, 1), "engine_flags": int(os.environ.get("GSTVD_ENGINE_FLAGS", "0")), "seed": 0}
     sl = dict(stream=torch.cuda.Stream(device=dev), start=start)
     vs, vf = enc_cfg.vocab_size, enc_cfg.v_feature_size
     if w in ("gen_teacher", "gen_qa_ppl"):
