@@ -448,6 +448,185 @@ dec_cross_tma2_kernel(const __grid_constant__ CUtensorMap tm, DecodeGeom g, int 
   }
 }
 
+// ---- third version: one WARP per (image, head) item, no block-wide synchronisation ------------------------------------
+// The 8-warp kernel above spends most of an item in its three block barriers, the cross-warp reduction of partial contexts
+// and the K -> scores -> V -> context chain of ONE item per CTA (profiles/r2_cross_phases.txt: ~1.5 us of math + ~1.5 us of
+// waiting per item, 2.6 items per CTA in sequence).  Here every warp owns a whole item: its K boxes and then its V boxes
+// (64 keys x 64 dims, 8 KB) stream through a private FIFO of kBufs buffers with one mbarrier each; the warp keeps ALL scores
+// of the item in registers (<= 19 key groups x 4 values per lane), takes the exact maximum, exponentiates in registers and
+// accumulates the context product in its own MMA accumulators - no shared-memory score tiles, no partial sums, no
+// __syncthreads.  Two 3-warp CTAs per SM (888 warp slots for the 768 items of a B = 64, 12-head step: one wave) keep
+// 6 x 24 KB of boxes in flight per SM; everything that does not depend on the query projection (barrier set-up, key count,
+// mask row, the first kBufs boxes) is done before the programmatic dependency is awaited.
+// Arithmetic: identical formulation to the kernel above (log2 domain, un-normalised bf16 probabilities <= 1, fp32
+// accumulation, one division at the end); the sums are taken in key order by one warp instead of per-warp partials.
+template <int kWarps, int kBufs>
+struct XwCfg {
+  static constexpr int kThreads = kWarps * 32;
+  static constexpr int kMaskFloats = kXtMaxBoxes * kXtRows;                       // 320: every fetched key has an entry
+  static constexpr int kWarpBytes = kBufs * kXtBoxBytes;
+  static constexpr int kSmem = kWarps * kWarpBytes + kWarps * kMaskFloats * 4 + kWarps * kBufs * 8 + 1024;
+};
+
+template <int kWarps, int kBufs>
+__global__ void __launch_bounds__(kWarps * 32, 2)
+dec_cross_warp_kernel(const __grid_constant__ CUtensorMap tm, DecodeGeom g, int layer, const bf16* __restrict__ q,
+                      const float* __restrict__ enc_mask, const int* __restrict__ cross_len, bf16* __restrict__ out) {
+  using Cfg = XwCfg<kWarps, kBufs>;
+  extern __shared__ uint8_t xw_raw[];
+  const uint32_t raw = smem_u32(xw_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = xw_raw + (base - raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int beam = lane >> 2, p4 = lane & 3, mi = lane >> 3;
+  const uint32_t buf0 = base + (uint32_t)warp * Cfg::kWarpBytes;
+  float* madd = reinterpret_cast<float*>(gen + kWarps * Cfg::kWarpBytes) + warp * Cfg::kMaskFloats;
+  const uint32_t bar0 = smem_u32(gen + kWarps * Cfg::kWarpBytes + kWarps * Cfg::kMaskFloats * 4) + (uint32_t)warp * kBufs * 8u;
+  const int items = g.B * g.heads;
+  if (lane == 0) {
+    if (warp == 0) tma_prefetch_desc(&tm);
+    for (int i = 0; i < kBufs; ++i) mbar_init(bar0 + 8u * i, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  pdl_launch_dependents();
+  const int nslots = gridDim.x * kWarps;
+  int item = warp * gridDim.x + blockIdx.x;                 // warp-major: the CTAs of one SM get equally many items
+  if (item >= items) return;
+
+  uint32_t seq = 0;                                          // FIFO element counter of this warp (buffer = seq % kBufs)
+  bool first = true;
+  const float sc = kLog2e / 8.0f;                            // scores / sqrt(64), log2 domain
+  for (; item < items; item += nslots) {
+    const int b = item / g.heads, h = item - b * g.heads;
+    int nk = cross_len ? cross_len[b] : g.Le;
+    nk = nk < 1 ? 1 : (nk > g.Le ? g.Le : nk);
+    const int nb = (nk + kXtRows - 1) / kXtRows;            // boxes of K (and of V)
+    const int ngroups = (nk + 15) >> 4;
+    const int nel = 2 * nb;                                  // FIFO elements of this item: K boxes, then V boxes
+    const int zk = ((layer * g.B + b) * 2 + 0) * g.heads + h, zv = zk + g.heads;
+    auto issue = [&](int el) {                               // lane 0
+      const uint32_t sl = (seq + (uint32_t)el) % kBufs;
+      const int kv = el >= nb, box = kv ? el - nb : el;
+      mbar_arrive_expect_tx(bar0 + 8u * sl, (uint32_t)kXtBoxBytes);
+      tma_load_3d(buf0 + sl * kXtBoxBytes, &tm, 0, box * kXtRows, kv ? zv : zk, bar0 + 8u * sl);
+    };
+    // cross K / V, cross_len and the mask date from the prefill: safe before the programmatic dependency resolves
+    if (lane == 0) {
+      const int pre = nel < kBufs ? nel : kBufs;
+      for (int el = 0; el < pre; ++el) issue(el);
+    }
+    for (int j = lane; j < Cfg::kMaskFloats; j += 32) {
+      const float m = (enc_mask && j < g.Le) ? enc_mask[(int64_t)b * g.Le + j] : 1.f;
+      madd[j] = (j < g.Le) ? (1.0f - m) * (-1e9f * kLog2e) : -INFINITY;
+    }
+    if (first) { pdl_wait(); first = false; }                // the query projection of this step is complete
+    uint32_t qa0[4], qa2[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) { qa0[kk] = 0u; qa2[kk] = 0u; }
+    if (beam < g.K) {
+      const bf16* qp = q + ((int64_t)(b * g.K + beam)) * g.H + h * 64 + p4 * 2;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        qa0[kk] = *reinterpret_cast<const uint32_t*>(qp + kk * 16);
+        qa2[kk] = *reinterpret_cast<const uint32_t*>(qp + kk * 16 + 8);
+      }
+    }
+    __syncwarp();                                            // mask row visible to the whole warp
+
+    // ---- phase A: scores of every key group, kept in registers: sv[G][0..1] keys 16G + p4*2 + {0,1}, sv[G][2..3] the same + 8 ----
+    float sv[kXtMaxBoxes * 4][4];
+    float mloc = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kXtMaxBoxes; ++j) {
+      if (j < nb) {
+        const uint32_t el = seq + (uint32_t)j;
+        mbar_wait(bar0 + 8u * (el % kBufs), (el / kBufs) & 1u);
+        const uint32_t kb_s = buf0 + (el % kBufs) * kXtBoxBytes;
+#pragma unroll
+        for (int gl = 0; gl < 4; ++gl) {
+          const int G = j * 4 + gl;
+          sv[G][0] = sv[G][1] = sv[G][2] = sv[G][3] = -INFINITY;
+          if (G < ngroups) {
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+            const int row = gl * 16 + (mi >> 1) * 8 + (lane & 7);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              uint32_t kb[4];
+              const int chunk = kk * 2 + (mi & 1);
+              ldmatrix_x4(kb, kb_s + row * 128 + ((chunk ^ (row & 7)) << 4));
+              mma_bf16_m8(c0, qa0[kk], qa2[kk], kb[0], kb[1]);
+              mma_bf16_m8(c1, qa0[kk], qa2[kk], kb[2], kb[3]);
+            }
+            const int key = G * 16 + p4 * 2;
+            const float2 m0 = *reinterpret_cast<const float2*>(madd + key), m1 = *reinterpret_cast<const float2*>(madd + key + 8);
+            sv[G][0] = fmaf(c0[0], sc, m0.x); sv[G][1] = fmaf(c0[1], sc, m0.y);
+            sv[G][2] = fmaf(c1[0], sc, m1.x); sv[G][3] = fmaf(c1[1], sc, m1.y);
+            mloc = fmaxf(fmaxf(mloc, fmaxf(sv[G][0], sv[G][1])), fmaxf(sv[G][2], sv[G][3]));
+          }
+        }
+        __syncwarp();                                        // every lane has read this box: the buffer may be refilled
+        if (lane == 0 && j + kBufs < nel) issue(j + kBufs);
+      } else {
+#pragma unroll
+        for (int gl = 0; gl < 4; ++gl) { const int G = j * 4 + gl; sv[G][0] = sv[G][1] = sv[G][2] = sv[G][3] = -INFINITY; }
+      }
+    }
+    mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 1));
+    mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 2));
+    // ---- probabilities (un-normalised, <= 1) as the A operand of the context product ----
+    uint32_t pa0[kXtMaxBoxes * 4], pa2[kXtMaxBoxes * 4];
+    float sloc = 0.f;
+#pragma unroll
+    for (int G = 0; G < kXtMaxBoxes * 4; ++G) {
+      const float e0 = ex2_approx(sv[G][0] - mloc), e1 = ex2_approx(sv[G][1] - mloc);
+      const float e2 = ex2_approx(sv[G][2] - mloc), e3 = ex2_approx(sv[G][3] - mloc);   // 2^(-inf) = 0: groups past the last key
+      sloc += (e0 + e1) + (e2 + e3);
+      __nv_bfloat162 lo = __floats2bfloat162_rn(e0, e1), hi = __floats2bfloat162_rn(e2, e3);
+      pa0[G] = *reinterpret_cast<uint32_t*>(&lo);
+      pa2[G] = *reinterpret_cast<uint32_t*>(&hi);
+    }
+    sloc += __shfl_xor_sync(0xffffffffu, sloc, 1);
+    sloc += __shfl_xor_sync(0xffffffffu, sloc, 2);
+    // ---- phase B: context O[beam][d] += P[beam][keys] V[keys][d] ----
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < kXtMaxBoxes; ++j) {
+      if (j < nb) {
+        const uint32_t el = seq + (uint32_t)(nb + j);
+        mbar_wait(bar0 + 8u * (el % kBufs), (el / kBufs) & 1u);
+        const uint32_t vb_s = buf0 + (el % kBufs) * kXtBoxBytes;
+#pragma unroll
+        for (int gl = 0; gl < 4; ++gl) {
+          const int G = j * 4 + gl;
+          if (G < ngroups) {
+            const int row = gl * 16 + (mi & 1) * 8 + (lane & 7);
+#pragma unroll
+            for (int dt = 0; dt < 8; dt += 2) {
+              uint32_t vb[4];
+              const int chunk = dt + (mi >> 1);
+              ldmatrix_x4_trans(vb, vb_s + row * 128 + ((chunk ^ (row & 7)) << 4));
+              mma_bf16_m8(o[dt], pa0[G], pa2[G], vb[0], vb[1]);
+              mma_bf16_m8(o[dt + 1], pa0[G], pa2[G], vb[2], vb[3]);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0 && nb + j + kBufs < nel) issue(nb + j + kBufs);
+      }
+    }
+    if (beam < g.K) {
+      bf16* op = out + ((int64_t)(b * g.K + beam)) * g.H + h * 64 + p4 * 2;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<__nv_bfloat162*>(op + dt * 8) = __floats2bfloat162_rn(o[dt][0] / sloc, o[dt][1] / sloc);
+    }
+    seq += (uint32_t)nel;
+    __syncwarp();                                            // the mask row is rewritten by the next item
+  }
+}
+
 // cross_len[b] = 1 + index of the last key whose mask is non-zero (Le when the whole row is masked: the reference then
 // spreads uniform weight over every key, which needs them all).
 __global__ void cross_len_kernel(int B, int Le, const float* __restrict__ mask, int* __restrict__ out) {
@@ -489,8 +668,9 @@ bool dec_cross_tma_supported(int dtype, const DecodeGeom& g) {
 
 int launch_dec_cross_tma(const DecodeGeom& g, int layer, const void* q, const void* cross_cache, const float* enc_mask,
                          const int* cross_len, void* out, int num_sms, cudaStream_t stream) {
-  // A/B aid: GSTVD_CROSS_TMA=1 scores through shared memory (first version), =3 one 16-warp CTA per SM with two stages
-  static const int variant = [] { const char* e = getenv("GSTVD_CROSS_TMA"); return e ? atoi(e) : 2; }();
+  // A/B aid: GSTVD_CROSS_TMA=1 scores through shared memory (first version), =2 two 8-warp CTAs per SM looping over items (round 1 / 2
+  // default), =3 one 16-warp CTA per SM with two stages, =4 (default) one warp per item
+  static const int variant = [] { const char* e = getenv("GSTVD_CROSS_TMA"); return e ? atoi(e) : 4; }();
   using Cfg2 = X2Cfg<8, 1, 3>;
   using Cfg3 = X2Cfg<16, 2, 2>;
   static bool configured = false;
@@ -504,6 +684,22 @@ int launch_dec_cross_tma(const DecodeGeom& g, int layer, const void* q, const vo
   const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(
       tma_map_rows3(cross_cache, 64, g.Le, (int64_t)g.layers * g.B * 2 * g.heads, kXtRows));
   const int items = g.B * g.heads;
+  if (variant == 4) {                                     // one warp per item (default)
+    // three boxes in flight per warp measured best (profiles/r2_cross_warp_ab.txt): 2 starve the warp, 4 leave no room on the SM for the
+    // look-ahead CTA of the following GEMM and take HBM bandwidth from its weight prefetch
+    using CfgW = XwCfg<3, 3>;
+    static bool configured_w = false;
+    if (!configured_w) {
+      cudaError_t e = cudaFuncSetAttribute(dec_cross_warp_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgW::kSmem);
+      if (e != cudaSuccess) throw std::runtime_error(std::string("dec_cross_warp: ") + cudaGetErrorString(e));
+      configured_w = true;
+    }
+    const int ctas = (items + 2) / 3;
+    const int grid_w = ctas < 2 * num_sms ? ctas : 2 * num_sms;
+    launch_k(dec_cross_warp_kernel<3, 3>, dim3(grid_w), dim3(CfgW::kThreads), (size_t)CfgW::kSmem, stream, *tm, g, layer, (const bf16*)q, enc_mask,
+             cross_len, (bf16*)out);
+    return 1;
+  }
   const int slots = variant == 3 ? num_sms : 2 * num_sms;
   const int grid = items < slots ? items : slots;
   static unsigned long long* d_stamps = nullptr;          // measurement aid: GSTVD_CROSS_TIMES=1, read back by dec_cross_print_times()
