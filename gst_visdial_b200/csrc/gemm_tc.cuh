@@ -153,10 +153,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.25 (|error| <= 2.5e-5, two orders of magnitude below
-// bf16 resolution) and approximate MUFU reciprocal / exp2: ~15 instructions per element instead of erff's ~35, so the GELU
-// epilogue of the FFN1 GEMM hides behind the MMA main loop.  (The fp32 parity path uses the exact erff in gemm_simt.cu.)
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)).  The epilogue of the FFN1 GEMMs is bound by issue slots (profiles/r2_pair_gemm_ncu_summary.txt:
+// ~6 100 warp instructions per scheduler and 128 x 256 tile against 6 144 tensor-pipe cycles), so what counts is instructions per element:
+//   default : erf(z) = tanh(z (a + b z^2 + c z^4)) with a minimax fit over z in [0, 5] (|error| <= 3.7e-5, tools/fit_erf_tanh.py) and the
+//             single-instruction MUFU tanh (relative error 2^-11): 8 instructions, |GELU error| <= 2.5e-4 |x| - an eighth of a bf16 ulp of
+//             the result for |x| >= 1/4 and below 2e-4 absolutely everywhere, i.e. far inside the rounding of the bf16 output it feeds;
+//   GSTVD_GELU_AS (compile-time, -DGSTVD_GELU_AS) : Abramowitz-Stegun 7.1.25 with MUFU reciprocal / exp2 (|error| <= 2.5e-5, ~15 instructions).
+// The fp32 parity path uses the exact erff (gemm_simt.cu).
 __device__ __forceinline__ float gelu_fast(float x) {
+#ifdef GSTVD_GELU_AS
   const float z = fabsf(x) * 0.70710678118654752440f;
   float t;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.47047f, z, 1.0f)));
@@ -168,6 +173,16 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float erf_abs = fmaf(-poly, e, 1.0f);
   const float erf = copysignf(erf_abs, x);
   return 0.5f * x * (1.0f + erf);
+#else
+  // z = x / sqrt 2;  u = z (a + b z^2 + c z^4) written in x:  a / sqrt2, b / sqrt2^3, c / sqrt2^5
+  const float x2 = fminf(x * x, 50.0f);                 // the fit covers |x| <= 7.07; beyond it tanh has saturated (and the quartic would turn over)
+  float q = fmaf(x2, -0.00031580700f, 0.036798256f);
+  q = fmaf(x2, q, 0.79771782f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * q));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+#endif
 }
 
 __device__ __forceinline__ int64_t out_index(const GemmArgs& p, int row, int col) {
