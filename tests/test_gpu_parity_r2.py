@@ -334,6 +334,35 @@ def test_cross_attention_more_items_than_warp_slots(tiny_cfgs, tiny_sd):
     assert agree_first >= 0.97 and agree_g >= 0.6, (agree_first, agree_g)
 
 
+def test_cross_attention_kernels_agree(full_cfgs, full_sd, monkeypatch):
+    """The two decode cross-attention kernels (one warp per item - default; 8-warp CTA per item, GSTVD_CROSS_TMA=2) implement the same
+    formulation and differ only in the order of the fp32 sums: full-size model, 3 images with histories of 40 / 150 / 256 tokens,
+    beam 5 and greedy - the first tokens must be identical and the sequences agree (near-ties may part ways later)."""
+    from gst_visdial_b200.engine import Engine
+    enc_cfg, dec_cfg = full_cfgs
+    B = 3
+    b = history_batch(enc_cfg, 0, B)
+    g = torch.Generator().manual_seed(5)
+    ids = b["enc_input_ids"]
+    for i, want in enumerate((40, 150, 256)):
+        n = int((ids[i] != 0).sum())
+        if want > n:
+            ids[i, n:want] = torch.randint(1000, enc_cfg.vocab_size, (want - n,), generator=g)
+    b["enc_att_mask"] = (ids != 0).float()
+    res = {}
+    for variant in ("4", "2"):
+        monkeypatch.setenv("GSTVD_CROSS_TMA", variant)
+        e = Engine(enc_cfg, dec_cfg, dtype="bf16", max_batch=B, max_beams=5)
+        e.load_state_dict(full_sd)
+        _enc(e, b, B)
+        res[variant] = (e.generate(B, num_beams=1, top_k=1).cpu(), e.generate(B, num_beams=5).cpu())
+        e.close()
+    for k in (0, 1):
+        assert torch.equal(res["4"][k][:, 0], res["2"][k][:, 0]), (res["4"][k][:, :4], res["2"][k][:, :4])
+        agree = (res["4"][k] == res["2"][k]).float().mean().item()
+        assert agree >= 0.6, agree
+
+
 def test_sampler_is_keyed_by_global_row(tiny_cfgs, tiny_sd):
     """the draws of an image must not depend on the batch / rank split.  The sampler is keyed by
     (seed, row_offset + row, step): four rows in one call == the same rows in two calls with row offsets 0 and 2, and
