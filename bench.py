@@ -472,6 +472,10 @@ def main():
     engines = [e for sl in slots for e in slot_engines(sl, dev)]
 
     def barrier():
+        # drain this rank's own queue BEFORE meeting the others: a rank with work still outstanding (rank 0 runs the decode-step
+        # roofline pass alone) would otherwise leave the collective, wait for its own GPU and start its timed region late - the
+        # other ranks then wait for it at the final all_gather and the max over ranks charges that skew to the step time
+        torch.cuda.synchronize(dev)
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize(dev)
