@@ -163,6 +163,11 @@ class EncoderDecoderModel(_EngineOwner, nn.Module):
         if dec_input_ids is None:
             return
         bos = int(getattr(self.decoder.config, "bos_token_id", 101) or 101)
+        eos = int(getattr(self.decoder.config, "eos_token_id", 102) or 102)
+        if bos != 101 or eos != 102:
+            # the engine's token bookkeeping (start token, [SEP] -> [PAD] in the prefix, end of hypothesis) uses the BERT ids the
+            # reference's configs carry (config/bert_base_6layer_6conect_dec.json: bos 101, eos 102)
+            raise NotImplementedError(f"the engine decodes with bos_token_id 101 / eos_token_id 102; the decoder config says {bos} / {eos}")
         if dec_input_ids.dim() != 2 or dec_input_ids.shape[1] != 1:
             raise ValueError(f"decode mode starts from one start token per row (dec_input_ids [B, 1]), got {tuple(dec_input_ids.shape)}")
         if not self._start_checked:
