@@ -336,6 +336,11 @@ def make_slot(a, si, rank, world, dev, local, enc_cfg, dec_cfg, sds):
     host = {k: v.pin_memory() for k, v in host.items()}
     sl["host"] = host
     sl["dev"] = {k: (v if k == "hist_len_bound" else v.to(dev)) for k, v in host.items()}      # the bound stays a host scalar
+    if w in ("gen_teacher", "gen_qa_ppl"):
+        # device-resident inputs: the caller keeps the (host-side) token counts the history bound is built from, like a loader that
+        # knows its caption lengths - otherwise every dialog would start with a device read that drains the slot's stream
+        sl["dev"]["enc_len_host"] = (host["enc_input_ids"] != 0).sum(-1).to(torch.int64)
+        sl["dev"]["questions_len_host"] = (host["questions"] != 0).sum(-1).to(torch.int64)
     return sl
 
 

@@ -44,6 +44,10 @@ def generate_dialogs(a_model, batch, q_model=None, questions=None, num_rounds=10
     (int64 [B, num_rounds, 18], zero padded, each ending in [SEP]) must be given.  ``a_kwargs`` / ``q_kwargs`` are the
     decoding kwargs of EncoderDecoderModel.forward; defaults are generate.py:138-141 / :177-180.
 
+    Optional keys ``enc_len_host`` (int64 [B], non-pad tokens of ``enc_input_ids``) and ``questions_len_host`` ([B, rounds]) are
+    HOST copies of the lengths the history bound starts from; with device-resident inputs they avoid the one device read (a stream
+    drain) at the start of a dialog.  They must be upper bounds of the true lengths.
+
     ``trim_history``: the encoder runs on ceil32(longest history) text positions instead of all ``max_seq_len`` (see
     ``enc_valid_len`` in EncoderDecoderModel.forward).  The bound is kept on the HOST - caption lengths are read once at the
     start, every round adds the question length (or ``max_new_tokens`` for a generated question) and ``max_new_tokens`` for
@@ -69,7 +73,9 @@ def generate_dialogs(a_model, batch, q_model=None, questions=None, num_rounds=10
     q_host = None                                               # [B, rounds] question lengths, read before the copy to the device
     if questions is not None:
         if trim_history and q_model is None:
-            q_host = (questions != 0).sum(-1).cpu().to(torch.int64)
+            q_host = batch.get("questions_len_host")            # optional: lengths the caller already holds on the host
+            if q_host is None:
+                q_host = (questions != 0).sum(-1).cpu().to(torch.int64)
         questions = questions.to(dtype=torch.int64, **nb)
     elif q_model is None:
         raise ValueError("generate_dialogs needs q_model or questions")
@@ -78,7 +84,10 @@ def generate_dialogs(a_model, batch, q_model=None, questions=None, num_rounds=10
     Lmax = st["ids"].shape[1]
     ub = None                                                   # host-side per-row upper bound of the history length
     if trim_history:
-        ub = (batch["enc_input_ids"] != 0).sum(-1).cpu().to(torch.int64)      # one read at the start (free for host inputs)
+        ub = batch.get("enc_len_host")                          # optional host copy of the caption lengths (int64 [B])
+        if ub is None:
+            ub = (batch["enc_input_ids"] != 0).sum(-1).cpu().to(torch.int64)  # one read at the start (free for host inputs)
+        ub = ub.to(torch.int64).clone()
 
     def bound():
         return int(ub.max().clamp(max=Lmax)) if ub is not None else None
