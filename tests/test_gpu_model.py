@@ -427,6 +427,27 @@ def test_history_trimming_is_exact(tiny_cfgs, tiny_sd):
         assert torch.equal(r1.answer_ppl.nan_to_num(-1.0), r0.answer_ppl.nan_to_num(-1.0)), dtype
 
 
+def test_dialog_host_length_hints_are_equivalent(tiny_cfgs, tiny_sd):
+    """Device-resident inputs + the optional host copies of the caption / question lengths (`enc_len_host`, `questions_len_host`:
+    no device read at the start of a dialog) give exactly what host inputs and plain device inputs give."""
+    from gst_visdial_b200 import synthetic as S, weights as W
+    from gst_visdial_b200.dialog import generate_dialogs
+    enc_cfg, dec_cfg = tiny_cfgs
+    a_model, _ = _build_model(W.TINY_ENC_CONFIG, W.TINY_DEC_CONFIG, tiny_sd, "bf16")
+    B, rounds = 4, 3
+    batch = S.synthetic_batch(0, B, vocab_size=enc_cfg.vocab_size, v_feature_size=enc_cfg.v_feature_size)
+    ques = torch.stack([torch.stack([S.synthetic_utterance(i, r, enc_cfg.vocab_size) for r in range(rounds)]) for i in range(B)])
+    kw = dict(temperature=1.0, top_k=1, top_p=0.0, ngram_blocking_size=0, num_beams=3)
+    ref = generate_dialogs(a_model, batch, questions=ques, num_rounds=rounds, a_kwargs=kw, with_ppl=True)
+    dev_batch = {k: v.cuda() for k, v in batch.items()}
+    plain = generate_dialogs(a_model, dev_batch, questions=ques.cuda(), num_rounds=rounds, a_kwargs=kw, with_ppl=True)
+    hinted = dict(dev_batch, enc_len_host=(batch["enc_input_ids"] != 0).sum(-1), questions_len_host=(ques != 0).sum(-1))
+    hint = generate_dialogs(a_model, hinted, questions=ques.cuda(), num_rounds=rounds, a_kwargs=kw, with_ppl=True)
+    for r in (plain, hint):
+        assert torch.equal(r.answers, ref.answers) and torch.equal(r.enc_input_ids, ref.enc_input_ids) and torch.equal(r.abnormal, ref.abnormal)
+        assert torch.equal(r.answer_ppl.nan_to_num(-1.0), ref.answer_ppl.nan_to_num(-1.0))
+
+
 def test_generate_cli_synthetic(tmp_path):
     """generate.py end to end (questioner + teacher, sampling with 4-gram blocking, ppl) on the tiny configs."""
     import json
