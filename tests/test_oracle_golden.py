@@ -65,3 +65,27 @@ def test_top_k_keeps_ties():
     x = torch.tensor([[0.1, 2.0, 2.0, -1.0]])
     y = R.top_k_top_p_filter(x.clone(), top_k=1)
     assert torch.isinf(y[0, 0]) and y[0, 1] == 2.0 and y[0, 2] == 2.0
+
+
+def test_decoding_utils_oracle_matches_reference_goldens(golden_dir):
+    """oracle/restatement.py `top_k_top_p_filter` (incl. the top_k = 0 / top_p > 0 branches) and `ngram_banned_tokens` against the
+    outputs of the reference's UNMODIFIED utils/decoding_utils.py (:4-35, :38-78) on seeded inputs, committed by
+    oracle/gen_golden_decoding.py - the GPU nucleus / full-vocabulary sampling tests check the kernels against these functions."""
+    import os
+    import numpy as np
+    from oracle import gen_golden_decoding as G
+    gold = np.load(os.path.join(golden_dir, "decoding_utils.npz"))
+    for i, (rows, V, k, p, _) in enumerate(G.FILTER_CASES):
+        x = G.filter_inputs(i)
+        keep = torch.isfinite(R.top_k_top_p_filter(x.clone(), top_k=k, top_p=p))
+        want = torch.from_numpy(np.unpackbits(gold[f"keep_{i}"], axis=-1)[:, :V].astype(bool))
+        assert torch.equal(keep, want), f"filter case {i} (top_k {k}, top_p {p})"
+        assert keep.sum(-1).tolist() == gold[f"kept_{i}"].tolist()
+        if p > 0:
+            assert int(keep[1].sum()) == 1                 # the peaked row: a one-token nucleus
+    for i, (rows, L, n, plen) in enumerate(G.NGRAM_CASES):
+        hist, prefix = G.ngram_inputs(i)
+        for r in range(rows):
+            got = sorted(set(R.ngram_banned_tokens(hist[r].tolist(), prefix[r].tolist(), n)))
+            want = [int(t) for t in gold[f"banned_{i}"][r] if t >= 0]
+            assert got == want, f"n-gram case {i} row {r}"
