@@ -13,7 +13,8 @@ Workloads (BASELINE.json `configs`; the default is configs[1], the configuration
                            sampling like generate.py:138-141,177-180, plus the answer-perplexity pass (generate.py:183-209);
                            global batch 256 over 8 GPUs = 32 images / GPU.  Unit: dialogs/s.
   select_data  configs[3]  -select_data scoring: teacher-forced perplexity of (context, 18-token answer) pairs
-                           (generate.py:183-209, dataloader_cc12m_gen.py:193-199), 64 pairs / GPU / step.  Unit: pairs/s.
+                           (generate.py:183-209, dataloader_cc12m_gen.py:193-199), 256 pairs / GPU / step (BASELINE.json names no batch
+                           for this config; 64 -> 256 raises the GEMM roofline from 0.55 to 0.78).  Unit: pairs/s.
   nsp_rank     configs[4]  enc_only_a discriminative ranking: 40 items x 100 candidate answers, every candidate its own
                            256-token encoder pass (evaluate_disc.py:66-83).  Unit: candidates/s.
 
@@ -53,7 +54,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="gen_teacher", choices=WORKLOADS)
-    ap.add_argument("--batch", type=int, default=0, help="units per GPU per forward (0: the workload's configuration: 64 / 32 / 64 / 40)")
+    ap.add_argument("--batch", type=int, default=0, help="units per GPU per forward (0: the workload's configuration: 64 / 32 / 256 / 40)")
     ap.add_argument("--rounds", type=int, default=10)
     ap.add_argument("--beams", type=int, default=5)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
@@ -66,7 +67,7 @@ def parse():
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall-clock cap of the reference arm")
     a = ap.parse_args()
     if a.batch <= 0:
-        a.batch = {"gen_teacher": 64, "gen_qa_ppl": 32, "select_data": 64, "nsp_rank": 40}[a.workload]
+        a.batch = {"gen_teacher": 64, "gen_qa_ppl": 32, "select_data": 256, "nsp_rank": 40}[a.workload]
     if a.streams <= 0:
         a.streams = 2 if a.workload.startswith("gen_") else 1
     return a
@@ -326,7 +327,7 @@ def make_slot(a, si, rank, world, dev, local, enc_cfg, dec_cfg, sds):
         host["answers"] = torch.stack([S.synthetic_utterance(start + i, 99, vs) for i in range(B)])
     else:
         from gst_visdial_b200.models.visual_dialog_encoder import VisualDialogEncoder
-        chunk = 500
+        chunk = 2000          # encoder passes per engine call: 500 -> 0.836 of the sustained bf16 rate, 1000 -> 0.855, 2000 -> 0.860 (same scores)
         p = dict(base, model="enc_only_a", mode="vd_eval_val", engine_max_batch=chunk)
         enc = VisualDialogEncoder(p)
         enc.load_state_dict({k[len("encoder."):]: v for k, v in sds["a"].items() if k.startswith("encoder.")})
