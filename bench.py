@@ -62,14 +62,14 @@ def parse():
                     help="run the encoder on all 256 history positions instead of ceil32(longest history) (A/B aid; results are identical)")
     ap.add_argument("--streams", type=int, default=0,
                     help="independent batches in flight per GPU (each on its own CUDA stream and engine context); 1 = strictly serial; "
-                         "0 = the workload's default (2 for the generation workloads, 1 for the tensor-bound ones)")
+                         "0 = the workload's default (gen_teacher 2, gen_qa_ppl 3, the tensor-bound ones 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall-clock cap of the reference arm")
     a = ap.parse_args()
     if a.batch <= 0:
         a.batch = {"gen_teacher": 64, "gen_qa_ppl": 32, "select_data": 256, "nsp_rank": 40}[a.workload]
     if a.streams <= 0:
-        a.streams = 2 if a.workload.startswith("gen_") else 1
+        a.streams = {"gen_teacher": 2, "gen_qa_ppl": 3}.get(a.workload, 1)      # measured: profiles/r2_scheduling_experiments.txt items 6, 10
     return a
 
 
